@@ -1,0 +1,82 @@
+"""ctypes binding of the C-ABI (include/effort_b200.h).  Fails loudly when the CUDA extension is
+missing: there is no CPU or PyTorch fallback for any operator in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_lib = None
+
+vp, fp, u32p = C.c_void_p, C.c_void_p, C.c_void_p
+
+
+class MulArgs(C.Structure):
+    _fields_ = [("v_dev", C.c_void_p), ("w", C.c_void_p), ("exp_no_dev", C.c_void_p),
+                ("out_dev", C.c_void_p), ("effort", C.c_double)]
+
+
+# name -> (restype, argtypes); every symbol include/effort_b200.h declares
+SIGNATURES = {
+    "effort_version": (C.c_int, []),
+    "effort_strerror": (C.c_char_p, [C.c_int]),
+    "effort_last_cuda_error": (C.c_char_p, []),
+    "effort_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "effort_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "effort_weights_create": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_uint, vp, C.POINTER(C.c_void_p)]),
+    "effort_weights_destroy": (C.c_int, [C.c_void_p]),
+    "effort_weights_owned_bytes": (C.c_size_t, [C.c_void_p]),
+    "effort_bucket_mul": (C.c_int, [vp, fp, vp, u32p, fp, C.c_double, vp]),
+    "effort_bucket_mul_q4": (C.c_int, [vp, fp, vp, u32p, fp, C.c_double, vp]),
+    "effort_expert_mul": (C.c_int, [vp, fp, vp, u32p, fp, C.c_double, vp]),
+    "effort_basic_mul": (C.c_int, [vp, fp, vp, C.c_int, C.c_int, fp, vp]),
+    "effort_expert_mul_batch": (C.c_int, [vp, C.POINTER(MulArgs), C.c_int, vp]),
+    "effort_calc_dispatch": (C.c_int, [vp, fp, vp, u32p, C.c_double, vp]),
+    "effort_mul": (C.c_int, [vp, vp, fp, vp]),
+    "effort_find_cutoff": (C.c_int, [vp, fp, vp, u32p, C.c_double, vp]),
+    "effort_read_dispatch": (C.c_int, [vp, vp, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                       C.POINTER(C.c_float), C.POINTER(C.c_int), vp]),
+    "effort_bucketize": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "effort_q4_bucketize": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "effort_launch_count": (C.c_uint64, []),
+    "effort_last_selected": (C.c_int, [vp, C.POINTER(C.c_uint32), vp]),
+}
+
+
+class EffortError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building if stale and nvcc is present) the native library.  Raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on the GPU box is fine iff the prebuilt .so travelled
+            if not os.path.exists(path):
+                raise EffortError(f"libeffort_b200.so is missing and cannot be built: {e}") from e
+    L = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        L = load()
+        msg = L.effort_strerror(rc).decode()
+        cu = L.effort_last_cuda_error().decode()
+        raise EffortError(f"{what}: {msg} (code {rc}){' [' + cu + ']' if cu and rc == -2 else ''}")

@@ -1,0 +1,445 @@
+// bucket_mul.cuh -- the gathered multiply-accumulate over the selected bucket rows.
+//
+// Reference kernels replaced: prepareDispatch (bucketMul.metal:47-79), roundUp/zeroRange32 (:11-31),
+// bucketMul (:83-117), bucketIntegrate (:122-137); Q4: prepareDispatchQ4 / bucketMulQ4
+// (bucketMulQ4.metal:25-92).
+//
+// B200 design:
+//  * HBM-bound gather, no tensor cores.  A bucket row is C 16-bit words; word (row r, column c) adds
+//    val_r * w into out[c*SLOTS + slot(w)] where slot is data dependent (4 position bits in the FP16
+//    mantissa; sign|pos nibbles in Q4).  The reference resolves the scatter with 16 predicated adds per
+//    weight (ALU bound at 50-70% of DRAM bandwidth, docs/gpu.html:183-187).  Here every WARP owns a
+//    private tile of fp32 accumulators in shared memory laid out [slot][k][lane], so that the
+//    read-modify-write of lane L always hits bank L: conflict free for any slot pattern, and -- because
+//    a lane owns its columns exclusively -- needs no atomics.
+//  * Warps are independent streams: no block barrier inside the streaming loop.  Each lane keeps U
+//    vector loads (8 or 16 bytes, L1::no_allocate) in flight.
+//  * Selection is fused: every CTA tests the stats of the input dims dealt to it (round robin, so the
+//    rank-major concentration of selected rows cannot unbalance CTAs), compacts (val,rowOffset) into a
+//    shared-memory list with ballot + prefix scan (deterministic order, no global atomics, no global
+//    dispatch list) and streams only those rows.
+//  * Cross-CTA reduction: CTA partial vectors + a tiny integrate kernel (deterministic).
+#pragma once
+#include "common.cuh"
+#include "cutoff.cuh"
+
+namespace effort {
+
+constexpr int kMulThreads = 512;  // 16 warps
+constexpr int kMulWarps = kMulThreads / 32;
+
+enum RowLayout : int {
+    kInputMajor = 0,  // row(e,i,rho) = (e*in + i)*P + rho      (device repack; Q4 native order)
+    kRankMajor = 1,   // row(e,i,rho) = e*P*in + rho*in + i      (reference FP16 order, convert.metal:96)
+};
+
+struct MulProblem {
+    const float* v;           // [in] fp32
+    const __half* st16;       // FP16 kind: one fp16 stat per row, same row order as `bk`
+    const float* st32;        // Q4 kind:   one fp32 stat (avg) per row
+    const uint16_t* bk;       // bucket rows [rows][C] 16-bit words
+    const __half* probes;     // [E][n_probes]
+    const uint32_t* exp_no;   // device scalar or null
+    const float* cutoff_in;   // precomputed cutoff (device) or null -> computed in-kernel
+    float* partial;           // [gridDim.x][out]
+    uint32_t* sel_counts;     // [gridDim.x] rows selected per CTA
+    float* cutoff_out;        // optional: CTA 0 stores the cutoff it used
+    int in, C, P, n_probes, q, layout;
+    int list_cap;             // capacity of the shared-memory row list (entries)
+};
+
+struct TileGeom {
+    int CT;             // column tiles per row
+    int S;              // row streams per CTA
+    int R;              // rows a warp processes per step (sub-warp rows when C is small)
+    int lanes_per_row;  // lanes covering one row inside a tile when R > 1 (else 32)
+};
+
+template <int VEC>
+__host__ __device__ inline TileGeom make_geom(int C) {
+    TileGeom g;
+    const int TW = 32 * VEC;
+    g.CT = (C + TW - 1) / TW;
+    if (g.CT > kMulWarps) g.CT = kMulWarps;  // guarded on the host (ESHAPE)
+    g.S = kMulWarps / g.CT;
+    g.R = 1;
+    g.lanes_per_row = 32;
+    if (g.CT == 1) {
+        int lpr = (C + VEC - 1) / VEC;
+        if (lpr <= 16 && (32 % lpr) == 0) { g.R = 32 / lpr; g.lanes_per_row = lpr; }
+    }
+    return g;
+}
+
+// ---- per-word accumulate ---------------------------------------------------------------------------
+// FP16 (SLOTS = 16): out[c*16 + (bits&15)] += val * float(w)       bucketMul.metal:100-106
+// Q4   (SLOTS = 32): for i=3..0: out[c*32 + i*8 + (w&7)] += (w&8) ? -val : val; w >>= 4
+//                                                                   bucketMulQ4.metal:78-83
+template <int SLOTS, int VEC>
+__device__ __forceinline__ void accumulate_words(float* __restrict__ tile, int lane, float val,
+                                                 const uint32_t (&words)[VEC / 2]) {
+    constexpr int TW = 32 * VEC;
+    if constexpr (SLOTS == 16) {
+        float a[VEC];
+        int idx[VEC];
+        float w[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC / 2; j++) {
+            const uint32_t r = words[j];
+            const __half2 h2 = *reinterpret_cast<const __half2*>(&r);
+            const float2 f2 = __half22float2(h2);
+            w[2 * j] = f2.x;
+            w[2 * j + 1] = f2.y;
+            idx[2 * j] = (int)(r & 15u) * TW + (2 * j) * 32 + lane;
+            idx[2 * j + 1] = (int)((r >> 16) & 15u) * TW + (2 * j + 1) * 32 + lane;
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; k++) a[k] = tile[idx[k]];
+#pragma unroll
+        for (int k = 0; k < VEC; k++) a[k] = fmaf(val, w[k], a[k]);
+#pragma unroll
+        for (int k = 0; k < VEC; k++) tile[idx[k]] = a[k];
+    } else {
+        // one 16-bit word = 4 nibbles that belong to 4 different 8-output groups: never alias
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+            uint32_t w = (words[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+            float a[4];
+            int idx[4];
+            float x[4];
+#pragma unroll
+            for (int i = 3; i >= 0; i--) {
+                x[i] = (w & 8u) ? -val : val;
+                idx[i] = (i * 8 + (int)(w & 7u)) * TW + k * 32 + lane;
+                w >>= 4;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = tile[idx[i]];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] += x[i];
+#pragma unroll
+            for (int i = 0; i < 4; i++) tile[idx[i]] = a[i];
+        }
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void load_words(const uint16_t* p, uint32_t (&words)[VEC / 2]) {
+    if constexpr (VEC == 8) {
+        uint4 d = ldg_stream_u4(p);
+        words[0] = d.x; words[1] = d.y; words[2] = d.z; words[3] = d.w;
+    } else if constexpr (VEC == 4) {
+        uint2 d = ldg_stream_u2(p);
+        words[0] = d.x; words[1] = d.y;
+    } else {
+        words[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+    }
+}
+
+// ---- streaming: one warp walks its share of the row list --------------------------------------------
+template <int SLOTS, int VEC, int U>
+__device__ __forceinline__ void stream_rows(const float* __restrict__ list_val,
+                                            const uint32_t* __restrict__ list_off, int n_list,
+                                            const uint16_t* __restrict__ bk, int C, const TileGeom g,
+                                            float* __restrict__ tile) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = warp % g.CT, s = warp / g.CT;
+    if (s >= g.S) return;  // spare warps when kMulWarps % CT != 0
+    const int rowslot = lane / g.lanes_per_row;
+    const int col = t * 32 * VEC + (lane % g.lanes_per_row) * VEC;
+    const bool lane_on = (col < C) && (rowslot < g.R);
+    const int stride = g.S * g.R;  // list entries consumed per step by all streams
+    const int first = s * g.R + rowslot;
+    const int nsteps = (n_list + stride - 1) / stride;
+    for (int n0 = 0; n0 < nsteps; n0 += U) {
+        uint32_t words[U][VEC / 2];
+        float val[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int e = (n0 + u) * stride + first;
+            ok[u] = lane_on && (e < n_list);
+            val[u] = 0.f;
+#pragma unroll
+            for (int j = 0; j < VEC / 2; j++) words[u][j] = 0u;
+            if (ok[u]) {
+                val[u] = list_val[e];
+                load_words<VEC>(bk + (size_t)list_off[e] + col, words[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (ok[u]) accumulate_words<SLOTS, VEC>(tile, lane, val[u], words[u]);
+    }
+}
+
+// ---- CTA epilogue: fold the warp tiles into one partial vector --------------------------------------
+template <int SLOTS, int VEC>
+__device__ __forceinline__ void reduce_tiles_to_partial(const float* __restrict__ tiles, int C,
+                                                        const TileGeom g, float* __restrict__ partial) {
+    constexpr int TW = 32 * VEC;
+    constexpr int TILE_FLOATS = SLOTS * TW;
+    const int out = C * SLOTS;
+    for (int o = threadIdx.x; o < out; o += blockDim.x) {
+        const int c = o / SLOTS, slot = o % SLOTS;
+        const int t = c / TW, cl = c % TW;
+        const int lane0 = cl / VEC, k = cl % VEC;
+        float sum = 0.f;
+        for (int s = 0; s < g.S; s++) {
+            const float* tile = tiles + (size_t)(s * g.CT + t) * TILE_FLOATS;
+            for (int rs = 0; rs < g.R; rs++)
+                sum += tile[slot * TW + k * 32 + rs * g.lanes_per_row + lane0];
+        }
+        partial[o] = sum;
+    }
+}
+
+struct MulSmemHeader {
+    CutoffSmem cut;
+    int warp_cnt[kMulWarps];
+    int n_list;
+    float cutoff;
+};
+
+// dynamic smem layout: [MulSmemHeader][list_val: cap floats][list_off: cap u32][tiles: kMulWarps*TILE_FLOATS]
+template <int SLOTS, int VEC>
+__host__ __device__ inline size_t mul_smem_bytes(int list_cap) {
+    size_t hdr = (sizeof(MulSmemHeader) + 15) & ~size_t(15);
+    return hdr + (size_t)list_cap * 8 + (size_t)kMulWarps * SLOTS * 32 * VEC * 4;
+}
+
+// ---- fused kernel: cutoff (optional) + selection + gather-MAC + CTA partial -------------------------
+template <int SLOTS, int VEC, int U>
+__global__ void __launch_bounds__(kMulThreads, 1)
+bucket_mul_fused_kernel(const MulProblem pb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MulSmemHeader& hdr = *reinterpret_cast<MulSmemHeader*>(smem_raw);
+    const size_t hdr_bytes = (sizeof(MulSmemHeader) + 15) & ~size_t(15);
+    float* list_val = reinterpret_cast<float*>(smem_raw + hdr_bytes);
+    uint32_t* list_off = reinterpret_cast<uint32_t*>(list_val + pb.list_cap);
+    float* tiles = reinterpret_cast<float*>(list_off + pb.list_cap);
+    constexpr int TILE_FLOATS = SLOTS * 32 * VEC;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t e_no = pb.exp_no ? *pb.exp_no : 0u;
+    const TileGeom g = make_geom<VEC>(pb.C);
+
+    // zero this warp's accumulator tile (independent of everything else: overlaps the loads below)
+    {
+        float4* t4 = reinterpret_cast<float4*>(tiles + (size_t)warp * TILE_FLOATS);
+        for (int i = lane; i < TILE_FLOATS / 4; i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    // 1. cutoff
+    float cutoff;
+    if (pb.cutoff_in) {
+        cutoff = *pb.cutoff_in;
+    } else {
+        float vals[kCutoffMaxPerThread * (kCutoffThreads / kMulThreads)];
+        score_probes(pb.v, pb.probes, e_no, pb.n_probes, vals);
+        cutoff = block_bisect_cutoff(vals, pb.n_probes, pb.q, hdr.cut, nullptr);
+    }
+    if (pb.cutoff_out && blockIdx.x == 0 && tid == 0) *pb.cutoff_out = cutoff;
+
+    // 2. selection: input dims i = blockIdx.x + j*gridDim.x; thread <-> (j, rho)
+    const int P = pb.P;
+    const int n_in = (pb.in > (int)blockIdx.x) ? (pb.in - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int n_rows = n_in * P;
+    int base = 0;
+    for (int r0 = 0; r0 < n_rows; r0 += kMulThreads) {
+        const int r = r0 + tid;
+        bool sel = false;
+        float val = 0.f;
+        uint32_t off = 0;
+        if (r < n_rows) {
+            const int j = r / P, rho = r % P;
+            const int i = (int)blockIdx.x + j * (int)gridDim.x;
+            const size_t row = (pb.layout == kInputMajor)
+                                   ? ((size_t)e_no * pb.in + i) * P + rho
+                                   : (size_t)e_no * P * pb.in + (size_t)rho * pb.in + i;
+            const float vi = pb.v[i];
+            float stat;
+            if constexpr (SLOTS == 16) stat = __half2float(pb.st16[row]);
+            else stat = pb.st32[row];
+            sel = row_selected(cutoff, stat, vi);
+            // Q4 payload is v*avg (bucketMulQ4.metal:51)
+            val = (SLOTS == 16) ? vi : __fmul_rn(vi, stat);
+            off = (uint32_t)(row * (size_t)pb.C);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, sel);
+        if (lane == 0) hdr.warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        int pre = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kMulWarps; w++) {
+            const int c = hdr.warp_cnt[w];
+            pre += (w < warp) ? c : 0;
+            tot += c;
+        }
+        if (sel) {
+            const int pos = base + pre + __popc(m & ((1u << lane) - 1u));
+            list_val[pos] = val;
+            list_off[pos] = off;
+        }
+        base += tot;
+        __syncthreads();
+    }
+    const int n_list = base;
+    if (pb.sel_counts && tid == 0) pb.sel_counts[blockIdx.x] = (uint32_t)n_list;
+    __syncthreads();  // list + zeroed tiles visible
+
+    // 3. stream the selected rows
+    stream_rows<SLOTS, VEC, U>(list_val, list_off, n_list, pb.bk, pb.C, g,
+                               tiles + (size_t)warp * TILE_FLOATS);
+    __syncthreads();
+
+    // 4. CTA partial
+    reduce_tiles_to_partial<SLOTS, VEC>(tiles, pb.C, g, pb.partial + (size_t)blockIdx.x * pb.C * SLOTS);
+}
+
+// ---- test-hook kernel: MAC over a reference-format dispatch list (BucketMul.mul) --------------------
+// dispatch: float2 {val, float(rowOffset)} in the reference's rank-major element offsets.
+template <int SLOTS, int VEC, int U>
+__global__ void __launch_bounds__(kMulThreads, 1)
+bucket_mul_dispatch_kernel(const uint16_t* __restrict__ bk, const float2* __restrict__ dispatch,
+                           const uint32_t* __restrict__ dispatch_size, int C, int list_cap,
+                           float* __restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const size_t hdr_bytes = (sizeof(MulSmemHeader) + 15) & ~size_t(15);
+    float* list_val = reinterpret_cast<float*>(smem_raw + hdr_bytes);
+    uint32_t* list_off = reinterpret_cast<uint32_t*>(list_val + list_cap);
+    float* tiles = reinterpret_cast<float*>(list_off + list_cap);
+    constexpr int TILE_FLOATS = SLOTS * 32 * VEC;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TileGeom g = make_geom<VEC>(C);
+    float4* t4 = reinterpret_cast<float4*>(tiles + (size_t)warp * TILE_FLOATS);
+    for (int i = lane; i < TILE_FLOATS / 4; i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // the reference splits the (padded) dispatch into 32 contiguous group slices (bucketMul.metal:94);
+    // here: contiguous slices per CTA, walked in chunks of list_cap entries.
+    const uint32_t n = *dispatch_size;
+    const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+    const uint32_t lo = min(n, per * blockIdx.x), hi = min(n, lo + per);
+    for (uint32_t c0 = lo; c0 < hi; c0 += (uint32_t)list_cap) {
+        const int m = (int)min((uint32_t)list_cap, hi - c0);
+        __syncthreads();
+        for (int i = tid; i < m; i += kMulThreads) {
+            const float2 d = dispatch[c0 + i];
+            list_val[i] = d.x;
+            list_off[i] = (uint32_t)d.y;  // int(d[1]), bucketMul.metal:98
+        }
+        __syncthreads();
+        stream_rows<SLOTS, VEC, U>(list_val, list_off, m, bk, C, g, tiles + (size_t)warp * TILE_FLOATS);
+    }
+    __syncthreads();
+    reduce_tiles_to_partial<SLOTS, VEC>(tiles, C, g, partial + (size_t)blockIdx.x * C * SLOTS);
+}
+
+// ---- integrate: out[o] (=|+=) sum_g partial[g][o]      (bucketIntegrate, bucketMul.metal:122-137) ---
+// accumulate != 0 keeps the Q4 semantics (atomic adds INTO out, bucketMulQ4.metal:89).
+__global__ void __launch_bounds__(256)
+integrate_kernel(const float* __restrict__ partial, int n_partials, int out, int accumulate,
+                 float* __restrict__ out_vec, const uint32_t* __restrict__ sel_counts,
+                 uint32_t* __restrict__ n_selected) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o < out) {
+        float s = 0.f;
+        for (int gq = 0; gq < n_partials; gq++) s += partial[(size_t)gq * out + o];
+        out_vec[o] = accumulate ? out_vec[o] + s : s;
+    }
+    if (n_selected && sel_counts && blockIdx.x == 0 && threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int gq = 0; gq < n_partials; gq++) t += sel_counts[gq];
+        *n_selected = t;
+    }
+}
+
+// ---- reference-format dispatch list (test hooks effort_calc_dispatch / effort_read_dispatch) --------
+// prepareDispatch / prepareDispatchQ4 with a deterministic (ascending row) order: pass 1 counts the
+// selected rows per chunk, pass 2 rescans and writes at the chunk's exclusive prefix.  Stats are read in
+// the REFERENCE layout here (half4 .w / float2 .y) because this is the bit-for-bit hook.
+constexpr int kDispChunk = 1024;
+
+template <int KIND>
+__device__ __forceinline__ bool ref_row_test(const void* stats, size_t i, const float* v, int in,
+                                             float cutoff, float& payload) {
+    if constexpr (KIND == 0) {
+        const float s = __half2float(reinterpret_cast<const __half*>(stats)[i * 4 + 3]);
+        const float val = v[i % (size_t)in];
+        payload = val;
+        return row_selected(cutoff, s, val);
+    } else {
+        const float s = reinterpret_cast<const float*>(stats)[i * 2 + 1];
+        const float val = v[i / 8];  // bucketMulQ4.metal:45
+        payload = __fmul_rn(val, s);
+        return row_selected(cutoff, s, val);
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kDispChunk)
+dispatch_count_kernel(const float* __restrict__ v, const void* __restrict__ stats,
+                      const uint32_t* __restrict__ exp_no, const float* __restrict__ cutoff, int in,
+                      int expert_size, uint32_t* __restrict__ chunk_counts) {
+    __shared__ int wc[32];
+    const uint32_t e_no = exp_no ? *exp_no : 0u;
+    const int r = blockIdx.x * kDispChunk + threadIdx.x;
+    bool sel = false;
+    float payload;
+    if (r < expert_size) sel = ref_row_test<KIND>(stats, (size_t)expert_size * e_no + r, v, in, *cutoff, payload);
+    const unsigned m = __ballot_sync(0xffffffffu, sel);
+    if ((threadIdx.x & 31) == 0) wc[threadIdx.x >> 5] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int c = warp_sum_i(wc[threadIdx.x]);
+        if (threadIdx.x == 0) chunk_counts[blockIdx.x] = (uint32_t)c;
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kDispChunk)
+dispatch_write_kernel(const float* __restrict__ v, const void* __restrict__ stats,
+                      const uint32_t* __restrict__ exp_no, const float* __restrict__ cutoff, int in, int C,
+                      int expert_size, const uint32_t* __restrict__ chunk_counts, int n_chunks,
+                      float2* __restrict__ dispatch, uint32_t* __restrict__ n_selected,
+                      uint32_t* __restrict__ padded_size, uint32_t* __restrict__ prev_size) {
+    __shared__ int wc[32];
+    __shared__ uint32_t s_base, s_total;
+    const uint32_t e_no = exp_no ? *exp_no : 0u;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // exclusive prefix of the chunk counts (n_chunks <= a few hundred)
+    if (warp == 0) {
+        uint32_t b = 0, t = 0;
+        for (int k = lane; k < n_chunks; k += 32) {
+            const uint32_t c = chunk_counts[k];
+            t += c;
+            if (k < (int)blockIdx.x) b += c;
+        }
+        b = (uint32_t)warp_sum_i((int)b);
+        t = (uint32_t)warp_sum_i((int)t);
+        if (lane == 0) { s_base = b; s_total = t; }
+    }
+    const int r = blockIdx.x * kDispChunk + tid;
+    bool sel = false;
+    float payload = 0.f;
+    size_t i = (size_t)expert_size * e_no + (size_t)r;
+    if (r < expert_size) sel = ref_row_test<KIND>(stats, i, v, in, *cutoff, payload);
+    const unsigned m = __ballot_sync(0xffffffffu, sel);
+    if (lane == 0) wc[warp] = __popc(m);
+    __syncthreads();
+    int pre = 0;
+    for (int w = 0; w < warp; w++) pre += wc[w];
+    if (sel) {
+        const uint32_t pos = s_base + pre + __popc(m & ((1u << lane) - 1u));
+        dispatch[pos] = make_float2(payload, (float)(uint32_t)(i * (size_t)C));  // float(i*colsCount), :71
+    }
+    // roundUp (bucketMul.metal:22-31) + zeroRange32 (:11-20): pad to (1 + n/2048)*2048 with {0,0}
+    const uint32_t total = s_total;
+    const uint32_t padded = (1u + total / 2048u) * 2048u;
+    if (blockIdx.x == 0) {
+        for (uint32_t p = total + tid; p < padded; p += kDispChunk) dispatch[p] = make_float2(0.f, 0.f);
+        if (tid == 0) { *n_selected = total; *prev_size = total; *padded_size = padded; }
+    }
+}
+
+}  // namespace effort

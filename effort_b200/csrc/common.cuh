@@ -1,0 +1,54 @@
+// common.cuh -- shared device helpers for the effort_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace effort {
+
+constexpr float kCutoffScale = 100000.0f;  // CUTOFF_SCALE, bucketMul.metal:33
+constexpr int kNumSMs = 148;               // B200
+
+// fp32 -> bfloat16 -> fp32, round-to-nearest-even; integer form so that it is bit-identical to the
+// oracle (Metal `bfloat(x)`, bucketMul.metal:160).
+__device__ __forceinline__ float bf16_round(float f) {
+    uint32_t x = __float_as_uint(f);
+    if ((x & 0x7FFFFFFFu) > 0x7F800000u) return __uint_as_float(x | 0x00400000u);
+    uint32_t lsb = (x >> 16) & 1u;
+    x += 0x7FFFu + lsb;
+    x &= 0xFFFF0000u;
+    return __uint_as_float(x);
+}
+
+__device__ __forceinline__ float half_bits_to_float(uint16_t b) {
+    return __half2float(__ushort_as_half(b));
+}
+
+// Selection predicate of prepareDispatch (bucketMul.metal:66): cutoff < CUTOFF_SCALE*float(stat)*|v|
+// evaluated left to right in fp32 (no fused contraction possible: two multiplies).
+__device__ __forceinline__ bool row_selected(float cutoff, float stat, float v) {
+    return cutoff < __fmul_rn(__fmul_rn(kCutoffScale, stat), fabsf(v));
+}
+
+// streaming 8/16-byte loads that do not allocate in L1 (weights are read once)
+__device__ __forceinline__ uint2 ldg_stream_u2(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
+                 : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ int warp_sum_i(int x) { return __reduce_add_sync(0xffffffffu, x); }
+__device__ __forceinline__ float warp_sum_f(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+}  // namespace effort

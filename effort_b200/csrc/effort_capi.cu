@@ -1,0 +1,520 @@
+// effort_capi.cu -- the C-ABI shim (include/effort_b200.h) over the sm_100a kernels.
+// Host orchestration here mirrors bucketMul.swift:34-88 / bucketMulQ4.swift:35-85 / expertMul.swift:20-38.
+#include "../../include/effort_b200.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "bucket_mul.cuh"
+#include "convert.cuh"
+#include "cutoff.cuh"
+
+using namespace effort;
+
+static std::atomic<uint64_t> g_launches{0};
+static thread_local std::string g_cuda_err;
+
+#define CK(expr)                                                                         \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            g_cuda_err = std::string(#expr) + ": " + cudaGetErrorString(_e);             \
+            return EFFORT_ECUDA;                                                         \
+        }                                                                                \
+    } while (0)
+#define LAUNCHED()                     \
+    do {                               \
+        g_launches.fetch_add(1);       \
+        CK(cudaGetLastError());        \
+    } while (0)
+
+struct effort_weights {
+    int in = 0, out = 0, n_experts = 1, P = 16, kind = EFFORT_KIND_FP16;
+    int n_probes = EFFORT_PROBES_COUNT;
+    int C = 0;  // 16-bit words per bucket row
+    unsigned flags = 0;
+    // caller-owned, reference layout
+    const uint16_t* buckets = nullptr;
+    const void* stats = nullptr;
+    const __half* probes = nullptr;
+    const float4* outliers = nullptr;
+    int n_outliers = 0;
+    const __half* core = nullptr;
+    // owned device copies
+    uint16_t* bk_own = nullptr;  // input-major rows (FP16 kind, unless NO_REPACK)
+    __half* st16 = nullptr;      // FP16: one stat per row (row order == fast-path bucket order)
+    float* st32 = nullptr;       // Q4
+    size_t owned = 0;
+    int layout = kInputMajor;
+    int device = 0;
+    const uint16_t* fast_bk() const { return bk_own ? bk_own : buckets; }
+};
+
+struct effort_ctx {
+    int device = 0;
+    int n_sms = kNumSMs;
+    // scratch
+    float* cutoff = nullptr;     // [kMaxBatch]
+    int* loops = nullptr;        // [1]
+    uint32_t* sizes = nullptr;   // [0]=n_selected [1]=padded [2]=prev  [3]=fused n_selected (+kMaxBatch)
+    float2* dispatch = nullptr;  // maxDispatchSize entries
+    size_t dispatch_cap = 0;
+    uint32_t* chunk_counts = nullptr;
+    size_t chunk_cap = 0;
+    float* partial = nullptr;
+    size_t partial_cap = 0;  // floats
+    uint32_t* sel_counts = nullptr;
+    size_t sel_cap = 0;
+    bool have_dispatch = false;
+    int dispatch_kind = 0;
+};
+
+static constexpr int kMaxBatch = 8;
+
+extern "C" int effort_version(void) { return EFFORT_B200_VERSION; }
+extern "C" const char* effort_last_cuda_error(void) { return g_cuda_err.c_str(); }
+extern "C" uint64_t effort_launch_count(void) { return g_launches.load(); }
+
+extern "C" const char* effort_strerror(int code) {
+    switch (code) {
+        case EFFORT_OK: return "ok";
+        case EFFORT_EINVAL: return "invalid argument / reference precondition failed";
+        case EFFORT_ECUDA: return "CUDA runtime error";
+        case EFFORT_ENOMEM: return "out of memory";
+        case EFFORT_ESHAPE: return "shape not supported by the kernels";
+        case EFFORT_ESTATE: return "call sequence error";
+        case EFFORT_ENOTLOADED: return "buckets not loaded and no dense core";
+        default: return "unknown error";
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+extern "C" int effort_ctx_create(int device, effort_ctx_t** ctx_out) {
+    if (!ctx_out) return EFFORT_EINVAL;
+    *ctx_out = nullptr;
+    int dev = device;
+    if (dev < 0) CK(cudaGetDevice(&dev));
+    else CK(cudaSetDevice(dev));
+    effort_ctx* c = new (std::nothrow) effort_ctx();
+    if (!c) return EFFORT_ENOMEM;
+    c->device = dev;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    c->n_sms = prop.multiProcessorCount;
+    CK(cudaMalloc(&c->cutoff, sizeof(float) * kMaxBatch));
+    CK(cudaMalloc(&c->loops, sizeof(int)));
+    CK(cudaMalloc(&c->sizes, sizeof(uint32_t) * (4 + kMaxBatch)));
+    CK(cudaMemset(c->sizes, 0, sizeof(uint32_t) * (4 + kMaxBatch)));
+    CK(cudaMemset(c->cutoff, 0, sizeof(float) * kMaxBatch));
+    CK(cudaMemset(c->loops, 0, sizeof(int)));
+    *ctx_out = c;
+    return EFFORT_OK;
+}
+
+extern "C" int effort_ctx_destroy(effort_ctx_t* c) {
+    if (!c) return EFFORT_OK;
+    cudaFree(c->cutoff); cudaFree(c->loops); cudaFree(c->sizes); cudaFree(c->dispatch);
+    cudaFree(c->chunk_counts); cudaFree(c->partial); cudaFree(c->sel_counts);
+    delete c;
+    return EFFORT_OK;
+}
+
+template <typename T>
+static int ensure(T*& p, size_t& cap, size_t need) {
+    if (need <= cap) return EFFORT_OK;
+    if (p) CK(cudaFree(p));
+    p = nullptr; cap = 0;
+    CK(cudaMalloc(&p, need * sizeof(T)));
+    cap = need;
+    return EFFORT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weights
+// ---------------------------------------------------------------------------------------------------
+extern "C" int effort_weights_create(const void* buckets_dev, const void* stats_dev, const void* probes_dev,
+                                     const void* outliers_dev, int n_outliers, const void* core_dev,
+                                     int in_dim, int out_dim, int n_experts, int percent_load, int kind,
+                                     unsigned flags, void* stream_, effort_weights_t** w_out) {
+    if (!w_out) return EFFORT_EINVAL;
+    *w_out = nullptr;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (in_dim <= 0 || out_dim <= 0 || n_experts <= 0) return EFFORT_EINVAL;
+    if (kind != EFFORT_KIND_FP16 && kind != EFFORT_KIND_Q4) return EFFORT_EINVAL;
+    const int bsize = kind == EFFORT_KIND_FP16 ? 16 : 8;
+    if (percent_load <= 0 || percent_load > bsize) return EFFORT_EINVAL;
+    if (!buckets_dev && !core_dev) return EFFORT_ENOTLOADED;
+    if (buckets_dev && (!stats_dev || !probes_dev)) return EFFORT_EINVAL;
+    const int words_div = kind == EFFORT_KIND_FP16 ? 16 : 32;
+    if (out_dim % words_div) return EFFORT_ESHAPE;
+    effort_weights* w = new (std::nothrow) effort_weights();
+    if (!w) return EFFORT_ENOMEM;
+    CK(cudaGetDevice(&w->device));
+    w->in = in_dim; w->out = out_dim; w->n_experts = n_experts; w->P = percent_load; w->kind = kind;
+    w->flags = flags; w->C = out_dim / words_div;
+    w->buckets = (const uint16_t*)buckets_dev; w->stats = stats_dev; w->probes = (const __half*)probes_dev;
+    w->outliers = (const float4*)outliers_dev; w->n_outliers = outliers_dev ? n_outliers : 0;
+    w->core = (const __half*)core_dev;
+    if (buckets_dev) {
+        // numBuckets % 4 == 0 is asserted by the reference (bucketMul.swift:76); the kernels need the
+        // row to be a whole number of 8-byte (FP16) / 4-byte (Q4) vectors.
+        if (kind == EFFORT_KIND_FP16 && (w->C % 4)) { delete w; return EFFORT_ESHAPE; }
+        if (kind == EFFORT_KIND_Q4 && (w->C % 2)) { delete w; return EFFORT_ESHAPE; }
+        const size_t rows = (size_t)n_experts * in_dim * percent_load;
+        if (rows * (size_t)w->C >= (size_t)1 << 32) { delete w; return EFFORT_ESHAPE; }
+        const int TB = 256;
+        if (kind == EFFORT_KIND_FP16) {
+            const bool repack = !(flags & EFFORT_WEIGHTS_NO_REPACK);
+            w->layout = repack ? kInputMajor : kRankMajor;
+            CK(cudaMalloc(&w->st16, rows * sizeof(__half)));
+            w->owned += rows * sizeof(__half);
+            repack_stats_fp16_kernel<<<(unsigned)((rows + TB - 1) / TB), TB, 0, stream>>>(
+                (const __half*)stats_dev, n_experts, in_dim, percent_load, repack ? 1 : 0, w->st16);
+            LAUNCHED();
+            if (repack) {
+                CK(cudaMalloc(&w->bk_own, rows * (size_t)w->C * 2));
+                w->owned += rows * (size_t)w->C * 2;
+                repack_rows_kernel<<<(unsigned)((rows * 32 + TB - 1) / TB), TB, 0, stream>>>(
+                    w->buckets, n_experts, in_dim, percent_load, w->C, w->bk_own);
+                LAUNCHED();
+            }
+        } else {
+            w->layout = kInputMajor;  // Q4 rows are already inIdx*8 + rank (q4_draft.py:150-168)
+            CK(cudaMalloc(&w->st32, rows * sizeof(float)));
+            w->owned += rows * sizeof(float);
+            repack_stats_q4_kernel<<<(unsigned)((rows + TB - 1) / TB), TB, 0, stream>>>(
+                (const float*)stats_dev, rows, w->st32);
+            LAUNCHED();
+        }
+    }
+    *w_out = w;
+    return EFFORT_OK;
+}
+
+extern "C" int effort_weights_destroy(effort_weights_t* w) {
+    if (!w) return EFFORT_OK;
+    cudaFree(w->bk_own); cudaFree(w->st16); cudaFree(w->st32);
+    delete w;
+    return EFFORT_OK;
+}
+extern "C" size_t effort_weights_owned_bytes(const effort_weights_t* w) { return w ? w->owned : 0; }
+
+// ---------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------
+static inline int effort_q(double effort, int n_probes) {
+    // let q = Int(Double(probesCount-1)*(1-effort))   bucketMul.swift:39
+    double x = (double)(n_probes - 1) * (1.0 - effort);
+    return (int)x;
+}
+
+static int check_mul_args(const effort_ctx* ctx, const float* v, const effort_weights* w, const float* out,
+                          double effort) {
+    if (!ctx || !v || !w || !out) return EFFORT_EINVAL;
+    if (!(effort >= 0.0 && effort <= 1.0)) return EFFORT_EINVAL;
+    return EFFORT_OK;
+}
+
+template <int SLOTS, int VEC, int U>
+static int launch_fused(effort_ctx* ctx, const MulProblem& pb, int grid, cudaStream_t stream) {
+    const size_t smem = mul_smem_bytes<SLOTS, VEC>(pb.list_cap);
+    static size_t configured = 0;
+    if (smem > configured) {
+        CK(cudaFuncSetAttribute(bucket_mul_fused_kernel<SLOTS, VEC, U>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    bucket_mul_fused_kernel<SLOTS, VEC, U><<<grid, kMulThreads, smem, stream>>>(pb);
+    LAUNCHED();
+    (void)ctx;
+    return EFFORT_OK;
+}
+
+// One fused bucketMul: [fused select+MAC kernel] -> [integrate].  slot = scratch slot inside a batch.
+static int enqueue_bucket_mul(effort_ctx* ctx, const float* v, const effort_weights* w, const uint32_t* exp_no,
+                              float* out, double effort, int accumulate, int slot, size_t partial_off,
+                              cudaStream_t stream) {
+    const int grid = ctx->n_sms;
+    MulProblem pb{};
+    pb.v = v; pb.st16 = w->st16; pb.st32 = w->st32; pb.bk = w->fast_bk(); pb.probes = w->probes;
+    pb.exp_no = exp_no; pb.cutoff_in = nullptr;
+    pb.partial = ctx->partial + partial_off;
+    pb.sel_counts = ctx->sel_counts + (size_t)slot * grid;
+    pb.cutoff_out = ctx->cutoff + slot;
+    pb.in = w->in; pb.C = w->C; pb.P = w->P; pb.n_probes = w->n_probes;
+    pb.q = effort_q(effort, w->n_probes);
+    pb.layout = w->layout;
+    const int per_cta = (w->in + grid - 1) / grid;
+    pb.list_cap = ((per_cta * w->P) + 3) & ~3;
+    int rc;
+    if (w->kind == EFFORT_KIND_FP16) {
+        if (make_geom<4>(w->C).CT * 128 < w->C) return EFFORT_ESHAPE;
+        rc = launch_fused<16, 4, 8>(ctx, pb, grid, stream);
+    } else {
+        if (make_geom<2>(w->C).CT * 64 < w->C) return EFFORT_ESHAPE;
+        rc = launch_fused<32, 2, 8>(ctx, pb, grid, stream);
+    }
+    if (rc) return rc;
+    integrate_kernel<<<(w->out + 255) / 256, 256, 0, stream>>>(pb.partial, grid, w->out, accumulate, out,
+                                                              pb.sel_counts, ctx->sizes + 3 + slot);
+    LAUNCHED();
+    return EFFORT_OK;
+}
+
+static int ensure_mul_scratch(effort_ctx* ctx, size_t partial_floats, int slots) {
+    int rc = ensure(ctx->partial, ctx->partial_cap, partial_floats);
+    if (rc) return rc;
+    return ensure(ctx->sel_counts, ctx->sel_cap, (size_t)slots * ctx->n_sms);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// operator entry points
+// ---------------------------------------------------------------------------------------------------
+extern "C" int effort_bucket_mul(effort_ctx_t* ctx, const float* v_dev, const effort_weights_t* w,
+                                 const uint32_t* exp_no_dev, float* out_dev, double effort, void* stream_) {
+    int rc = check_mul_args(ctx, v_dev, w, out_dev, effort);
+    if (rc) return rc;
+    if (w->kind != EFFORT_KIND_FP16) return EFFORT_EINVAL;  // assert(!goQ8...) bucketMul.swift:72
+    if (!w->buckets) return EFFORT_ENOTLOADED;
+    rc = ensure_mul_scratch(ctx, (size_t)ctx->n_sms * w->out, kMaxBatch);
+    if (rc) return rc;
+    return enqueue_bucket_mul(ctx, v_dev, w, exp_no_dev, out_dev, effort, 0, 0, 0, (cudaStream_t)stream_);
+}
+
+static int enqueue_outliers(const float* v, const effort_weights* w, float* out, cudaStream_t stream) {
+    if (w->outliers && w->n_outliers > 0) {
+        calc_outliers_kernel<<<(w->n_outliers + 255) / 256, 256, 0, stream>>>(v, w->outliers, w->n_outliers, out);
+        LAUNCHED();
+    }
+    return EFFORT_OK;
+}
+
+extern "C" int effort_bucket_mul_q4(effort_ctx_t* ctx, const float* v_dev, const effort_weights_t* w,
+                                    const uint32_t* exp_no_dev, float* out_dev, double effort, void* stream_) {
+    int rc = check_mul_args(ctx, v_dev, w, out_dev, effort);
+    if (rc) return rc;
+    if (w->kind != EFFORT_KIND_Q4) return EFFORT_EINVAL;
+    if (!w->buckets) return EFFORT_ENOTLOADED;
+    rc = ensure_mul_scratch(ctx, (size_t)ctx->n_sms * w->out, kMaxBatch);
+    if (rc) return rc;
+    // bucketMulQ4 accumulates into out (atomics, bucketMulQ4.metal:89), then calcOutliers (:61)
+    rc = enqueue_bucket_mul(ctx, v_dev, w, exp_no_dev, out_dev, effort, 1, 0, 0, (cudaStream_t)stream_);
+    if (rc) return rc;
+    return enqueue_outliers(v_dev, w, out_dev, (cudaStream_t)stream_);
+}
+
+static int enqueue_basic_mul(const float* v, const __half* core, int out_dim, int in_dim, float* out,
+                             int n_sms, cudaStream_t stream) {
+    if (in_dim % 16) return EFFORT_EINVAL;  // assert(weights.cols % 16 == 0) mps.swift:18
+    const size_t smem = (size_t)in_dim * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        CK(cudaFuncSetAttribute(basic_mul_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int grid = (out_dim + 7) / 8;
+    const int max_grid = n_sms * 8;
+    if (grid > max_grid) grid = max_grid;
+    basic_mul_kernel<<<grid, 256, smem, stream>>>(v, core, out_dim, in_dim, out);
+    LAUNCHED();
+    return EFFORT_OK;
+}
+
+extern "C" int effort_basic_mul(effort_ctx_t* ctx, const float* v_dev, const void* core_dev, int out_dim,
+                                int in_dim, float* out_dev, void* stream_) {
+    if (!ctx || !v_dev || !core_dev || !out_dev || out_dim <= 0 || in_dim <= 0) return EFFORT_EINVAL;
+    if ((size_t)in_dim * sizeof(float) > 200 * 1024) return EFFORT_ESHAPE;
+    return enqueue_basic_mul(v_dev, (const __half*)core_dev, out_dim, in_dim, out_dev, ctx->n_sms,
+                             (cudaStream_t)stream_);
+}
+
+static int expert_mul_one(effort_ctx* ctx, const effort_mul_args_t& a, int slot, size_t partial_off,
+                          cudaStream_t stream) {
+    const effort_weights* w = a.w;
+    if (w->kind == EFFORT_KIND_Q4) {  // expertMul.swift:25-31
+        if (w->buckets) {
+            CK(cudaMemsetAsync(a.out_dev, 0, sizeof(float) * w->out, stream));  // out.zero()
+            int rc = enqueue_bucket_mul(ctx, a.v_dev, w, a.exp_no_dev, a.out_dev, a.effort, 1, slot, partial_off, stream);
+            if (rc) return rc;
+            return enqueue_outliers(a.v_dev, w, a.out_dev, stream);
+        }
+        if (!w->core) return EFFORT_ENOTLOADED;
+        return enqueue_basic_mul(a.v_dev, w->core, w->out, w->in, a.out_dev, ctx->n_sms, stream);
+    }
+    if (!w->buckets) return EFFORT_ENOTLOADED;
+    return enqueue_bucket_mul(ctx, a.v_dev, w, a.exp_no_dev, a.out_dev, a.effort, 0, slot, partial_off, stream);
+}
+
+extern "C" int effort_expert_mul_batch(effort_ctx_t* ctx, const effort_mul_args_t* args, int n, void* stream_) {
+    if (!ctx || !args || n <= 0 || n > kMaxBatch) return EFFORT_EINVAL;
+    size_t total = 0;
+    for (int k = 0; k < n; k++) {
+        int rc = check_mul_args(ctx, args[k].v_dev, args[k].w, args[k].out_dev, args[k].effort);
+        if (rc) return rc;
+        total += (size_t)ctx->n_sms * args[k].w->out;
+    }
+    int rc = ensure_mul_scratch(ctx, total, kMaxBatch);
+    if (rc) return rc;
+    size_t off = 0;
+    for (int k = 0; k < n; k++) {
+        rc = expert_mul_one(ctx, args[k], k, off, (cudaStream_t)stream_);
+        if (rc) return rc;
+        off += (size_t)ctx->n_sms * args[k].w->out;
+    }
+    return EFFORT_OK;
+}
+
+extern "C" int effort_expert_mul(effort_ctx_t* ctx, const float* v_dev, const effort_weights_t* w,
+                                 const uint32_t* exp_no_dev, float* out_dev, double effort, void* stream_) {
+    effort_mul_args_t a{v_dev, w, exp_no_dev, out_dev, effort};
+    return effort_expert_mul_batch(ctx, &a, 1, stream_);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// test hooks
+// ---------------------------------------------------------------------------------------------------
+extern "C" int effort_find_cutoff(effort_ctx_t* ctx, const float* v_dev, const effort_weights_t* w,
+                                  const uint32_t* exp_no_dev, double effort, void* stream_) {
+    if (!ctx || !v_dev || !w || !w->probes) return EFFORT_EINVAL;
+    if (!(effort >= 0.0 && effort <= 1.0)) return EFFORT_EINVAL;
+    if (w->n_probes > kCutoffThreads * kCutoffMaxPerThread) return EFFORT_ESHAPE;
+    find_cutoff_kernel<<<1, kCutoffThreads, 0, (cudaStream_t)stream_>>>(
+        v_dev, w->probes, exp_no_dev, w->n_probes, effort_q(effort, w->n_probes), ctx->cutoff, ctx->loops);
+    LAUNCHED();
+    return EFFORT_OK;
+}
+
+extern "C" int effort_calc_dispatch(effort_ctx_t* ctx, const float* v_dev, const effort_weights_t* w,
+                                    const uint32_t* exp_no_dev, double effort, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!ctx || !v_dev || !w) return EFFORT_EINVAL;
+    if (!w->buckets) return EFFORT_ENOTLOADED;
+    int rc = effort_find_cutoff(ctx, v_dev, w, exp_no_dev, effort, stream_);
+    if (rc) return rc;
+    const int expert_size = w->P * w->in;  // loader.swift:50
+    // assert(dispatch.rows >= ew.buckets.rows*2) bucketMul.swift:35 -> grow instead
+    rc = ensure(ctx->dispatch, ctx->dispatch_cap, (size_t)expert_size + 2048);
+    if (rc) return rc;
+    const int n_chunks = (expert_size + kDispChunk - 1) / kDispChunk;
+    rc = ensure(ctx->chunk_counts, ctx->chunk_cap, (size_t)n_chunks);
+    if (rc) return rc;
+    if (w->kind == EFFORT_KIND_FP16) {
+        dispatch_count_kernel<0><<<n_chunks, kDispChunk, 0, stream>>>(v_dev, w->stats, exp_no_dev, ctx->cutoff,
+                                                                      w->in, expert_size, ctx->chunk_counts);
+        LAUNCHED();
+        dispatch_write_kernel<0><<<n_chunks, kDispChunk, 0, stream>>>(
+            v_dev, w->stats, exp_no_dev, ctx->cutoff, w->in, w->C, expert_size, ctx->chunk_counts, n_chunks,
+            ctx->dispatch, ctx->sizes + 0, ctx->sizes + 1, ctx->sizes + 2);
+        LAUNCHED();
+    } else {
+        dispatch_count_kernel<1><<<n_chunks, kDispChunk, 0, stream>>>(v_dev, w->stats, exp_no_dev, ctx->cutoff,
+                                                                      w->in, expert_size, ctx->chunk_counts);
+        LAUNCHED();
+        dispatch_write_kernel<1><<<n_chunks, kDispChunk, 0, stream>>>(
+            v_dev, w->stats, exp_no_dev, ctx->cutoff, w->in, w->C, expert_size, ctx->chunk_counts, n_chunks,
+            ctx->dispatch, ctx->sizes + 0, ctx->sizes + 1, ctx->sizes + 2);
+        LAUNCHED();
+    }
+    ctx->have_dispatch = true;
+    ctx->dispatch_kind = w->kind;
+    return EFFORT_OK;
+}
+
+template <int SLOTS, int VEC, int U>
+static int launch_dispatch_mac(effort_ctx* ctx, const effort_weights* w, int grid, int list_cap,
+                               cudaStream_t stream) {
+    const size_t smem = mul_smem_bytes<SLOTS, VEC>(list_cap);
+    static size_t configured = 0;
+    if (smem > configured) {
+        CK(cudaFuncSetAttribute(bucket_mul_dispatch_kernel<SLOTS, VEC, U>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    bucket_mul_dispatch_kernel<SLOTS, VEC, U><<<grid, kMulThreads, smem, stream>>>(
+        w->buckets, ctx->dispatch, ctx->sizes + 1, w->C, list_cap, ctx->partial);
+    LAUNCHED();
+    return EFFORT_OK;
+}
+
+extern "C" int effort_mul(effort_ctx_t* ctx, const effort_weights_t* w, float* out_dev, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!ctx || !w || !out_dev) return EFFORT_EINVAL;
+    if (!ctx->have_dispatch || ctx->dispatch_kind != w->kind) return EFFORT_ESTATE;
+    if (!w->buckets) return EFFORT_ENOTLOADED;
+    const int grid = ctx->n_sms;
+    int rc = ensure_mul_scratch(ctx, (size_t)grid * w->out, kMaxBatch);
+    if (rc) return rc;
+    const int list_cap = 2048;
+    if (w->kind == EFFORT_KIND_FP16) rc = launch_dispatch_mac<16, 4, 8>(ctx, w, grid, list_cap, stream);
+    else rc = launch_dispatch_mac<32, 2, 8>(ctx, w, grid, list_cap, stream);
+    if (rc) return rc;
+    integrate_kernel<<<(w->out + 255) / 256, 256, 0, stream>>>(ctx->partial, grid, w->out,
+                                                              w->kind == EFFORT_KIND_Q4 ? 1 : 0, out_dev,
+                                                              nullptr, nullptr);
+    LAUNCHED();
+    return EFFORT_OK;
+}
+
+extern "C" int effort_read_dispatch(effort_ctx_t* ctx, float* dispatch_host, size_t capacity,
+                                    uint32_t* n_selected, uint32_t* padded_size, float* cutoff,
+                                    int* cutoff_loops, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!ctx) return EFFORT_EINVAL;
+    CK(cudaStreamSynchronize(stream));
+    uint32_t sizes[3] = {0, 0, 0};
+    CK(cudaMemcpy(sizes, ctx->sizes, sizeof(sizes), cudaMemcpyDeviceToHost));
+    if (n_selected) *n_selected = sizes[0];
+    if (padded_size) *padded_size = sizes[1];
+    if (cutoff) CK(cudaMemcpy(cutoff, ctx->cutoff, sizeof(float), cudaMemcpyDeviceToHost));
+    if (cutoff_loops) CK(cudaMemcpy(cutoff_loops, ctx->loops, sizeof(int), cudaMemcpyDeviceToHost));
+    if (dispatch_host && ctx->have_dispatch) {
+        size_t n = sizes[1] < capacity ? sizes[1] : capacity;
+        if (n) CK(cudaMemcpy(dispatch_host, ctx->dispatch, n * sizeof(float2), cudaMemcpyDeviceToHost));
+    }
+    return EFFORT_OK;
+}
+
+extern "C" int effort_last_selected(effort_ctx_t* ctx, uint32_t* n_selected, void* stream_) {
+    if (!ctx || !n_selected) return EFFORT_EINVAL;
+    CK(cudaStreamSynchronize((cudaStream_t)stream_));
+    CK(cudaMemcpy(n_selected, ctx->sizes + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return EFFORT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// convert
+// ---------------------------------------------------------------------------------------------------
+extern "C" int effort_bucketize(const void* w_dev, int out_dim, int in_dim, void* buckets_dev, void* stats_dev,
+                                void* probes_dev, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!w_dev || !buckets_dev || !stats_dev || !probes_dev) return EFFORT_EINVAL;
+    const int NP = EFFORT_PROBES_COUNT;
+    // preconditions, convert.swift:210-215
+    if (!(out_dim >= NP || (out_dim > 0 && NP % out_dim == 0))) return EFFORT_EINVAL;
+    if (in_dim < NP) return EFFORT_EINVAL;
+    if (out_dim > 32000 || in_dim > 32000) return EFFORT_EINVAL;
+    if (out_dim % 16) return EFFORT_EINVAL;  // assert(outDim % bSize == 0) :239
+    const int rep = out_dim >= NP ? 1 : NP / out_dim;
+    get_probes_kernel<<<(NP / rep + 255) / 256, 256, 0, stream>>>((const uint16_t*)w_dev, in_dim, rep, NP,
+                                                                 (uint16_t*)probes_dev);
+    LAUNCHED();
+    const int C = out_dim / 16;
+    dim3 grid((in_dim + 31) / 32, (C + 31) / 32);
+    bucketize_kernel<<<grid, 1024, 0, stream>>>((const uint16_t*)w_dev, out_dim, in_dim, (uint16_t*)buckets_dev);
+    LAUNCHED();
+    const size_t rows = (size_t)in_dim * 16;
+    make_stats_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, stream>>>((const uint16_t*)buckets_dev, rows, C,
+                                                                          (__half*)stats_dev);
+    LAUNCHED();
+    return EFFORT_OK;
+}
+
+extern "C" int effort_q4_bucketize(const void*, int, int, void*, void*, void*, void*) {
+    return EFFORT_ESHAPE;  // implemented in a later milestone (q4.cuh)
+}

@@ -1,0 +1,164 @@
+/*
+ * effort_b200.h -- C-ABI of the B200-native bucketMul hot path.
+ *
+ * Drop-in boundary for kolinko/effort's approximate GEMV.  The reference has no
+ * FFI layer today: its boundary is a handful of Swift free functions plus the
+ * deliberately non-private BucketMul.shared test hooks.  Each entry point below
+ * names the reference interface (file:line under the reference checkout) that
+ * it replaces.  All pointers named *_dev are CUDA device pointers; `stream` is
+ * a cudaStream_t passed as void* (0 = legacy default stream).  Every call that
+ * takes a stream only ENQUEUES work on it (the reference's gpu.deploy is
+ * enqueue-only, helpers/gpu.swift:135-196; completion = gpu.eval(), :109-119).
+ * All functions return 0 or a negative EFFORT_E* code; nothing aborts (the
+ * reference asserts, bucketMul.swift:35-36).
+ *
+ * No torch / C++ types cross this boundary.  The library fails at load time if
+ * the CUDA runtime is missing; there is no CPU fallback.
+ */
+#ifndef EFFORT_B200_H
+#define EFFORT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EFFORT_B200_VERSION 100
+
+/* error codes */
+#define EFFORT_OK 0
+#define EFFORT_EINVAL (-1)    /* bad argument / failed reference precondition  */
+#define EFFORT_ECUDA (-2)     /* CUDA runtime error (see effort_last_cuda_error) */
+#define EFFORT_ENOMEM (-3)
+#define EFFORT_ESHAPE (-4)    /* shape outside what the kernels support          */
+#define EFFORT_ESTATE (-5)    /* e.g. effort_mul without a prior calc_dispatch    */
+#define EFFORT_ENOTLOADED (-6)/* buckets not loaded and no dense core to fall back on */
+
+/* weight kinds: main.swift:49-51 globals goQ4 / goQ8 (Q8 asserts false, expertMul.swift:33-36) */
+#define EFFORT_KIND_FP16 0
+#define EFFORT_KIND_Q4 1
+
+/* effort_weights_create flags */
+#define EFFORT_WEIGHTS_DEFAULT 0u
+/* keep using the caller's rank-major buffers for the fast path too (no input-major device repack;
+ * slower gathers, zero extra memory).  Without it the library builds its own repacked copy and the
+ * caller's buckets/stats are only needed again by the effort_calc_dispatch/effort_mul test hooks. */
+#define EFFORT_WEIGHTS_NO_REPACK 1u
+
+#define EFFORT_PROBES_COUNT 4096 /* bucketMul.swift:19, loader.swift:66 */
+
+typedef struct effort_ctx effort_ctx_t;         /* replaces the BucketMul.shared / BucketMulQ4.shared singletons
+                                                   (bucketMul.swift:18-32): per-context scratch, one stream at a time */
+typedef struct effort_weights effort_weights_t; /* replaces class ExpertWeights (loader.swift:46-167) */
+
+/* ---- library ---------------------------------------------------------- */
+int effort_version(void);
+const char* effort_strerror(int code);
+/* text of the last CUDA error seen by this thread's calls ("" if none) */
+const char* effort_last_cuda_error(void);
+
+/* ---- context ---------------------------------------------------------- */
+/* Scratch: dispatch list (maxDispatchSize = 229376*2 float2 entries, bucketMul.swift:20-29),
+ * cutoff scalar, partial-sum buffer (tmpMulVec [32,16384], bucketMul.swift:52 -> here [nCTA, out]).
+ * `device` = CUDA device ordinal (-1 = current). */
+int effort_ctx_create(int device, effort_ctx_t** ctx_out);
+int effort_ctx_destroy(effort_ctx_t* ctx);
+
+/* ---- weights ---------------------------------------------------------- */
+/*
+ * ExpertWeights (loader.swift:46-167).  Shapes as the reference stores them:
+ *   FP16: buckets [n_experts, in*percent_load, out/16] f16    stats [n_experts, in*percent_load, 4] f16
+ *   Q4:   buckets [n_experts, in*8, out/32] u16 (viewed f16)  stats [n_experts, in*8, 2] f32
+ *   probes [n_experts, 4096] f16;  outliers [n_outliers, 4] f32 or NULL (Q4);
+ *   core [out, in] f16 or NULL (dense fallback, expertMul.swift:29-31).
+ * percent_load = number of rank rows kept per input dim (16 = all, loader.swift:50,157-159); Q4 uses 8.
+ * buckets_dev may be NULL only when core_dev is given ("buckets not loaded", loader.swift:105-108).
+ * The handle never owns the caller's buffers.
+ */
+int effort_weights_create(const void* buckets_dev, const void* stats_dev, const void* probes_dev,
+                          const void* outliers_dev, int n_outliers, const void* core_dev,
+                          int in_dim, int out_dim, int n_experts, int percent_load, int kind,
+                          unsigned flags, void* stream, effort_weights_t** w_out);
+int effort_weights_destroy(effort_weights_t* w);
+/* bytes of device memory the handle owns (the repacked copy) */
+size_t effort_weights_owned_bytes(const effort_weights_t* w);
+
+/* ---- the operator ------------------------------------------------------ */
+/*
+ * bucketMul(v:by:expNo:out:effort:)  bucketMul.swift:11  (FP16; overwrites out, bucketMul.metal:133)
+ *   v_dev [in] f32, out_dev [out] f32, exp_no_dev: device uint32 (NULL = expert 0,
+ *   expertMul.swift:18), effort in [0,1] (default 0.25 in the reference).
+ */
+int effort_bucket_mul(effort_ctx_t* ctx, const float* v_dev, const effort_weights_t* w,
+                      const uint32_t* exp_no_dev, float* out_dev, double effort, void* stream);
+/* bucketMulQ4(v:by:expNo:out:effort:)  bucketMulQ4.swift:11  (accumulates INTO out, then calcOutliers) */
+int effort_bucket_mul_q4(effort_ctx_t* ctx, const float* v_dev, const effort_weights_t* w,
+                         const uint32_t* exp_no_dev, float* out_dev, double effort, void* stream);
+/* expertMul(v:by:expNo:out:effort:)  expertMul.swift:24-38: Q4 -> out.zero(); bucketMulQ4 if buckets
+ * loaded else basicMul(core); FP16 -> bucketMul. */
+int effort_expert_mul(effort_ctx_t* ctx, const float* v_dev, const effort_weights_t* w,
+                      const uint32_t* exp_no_dev, float* out_dev, double effort, void* stream);
+/* basicMul(v:by:out:)  helpers/mps.swift:14-47: dense fp16 [out,in] x fp16(v) -> fp32 out */
+int effort_basic_mul(effort_ctx_t* ctx, const float* v_dev, const void* core_dev, int out_dim, int in_dim,
+                     float* out_dev, void* stream);
+
+/*
+ * Several bucketMuls that do not depend on each other (q/k/v share v, runNetwork.swift:132-134;
+ * w1/w3, :178-179) enqueued as ONE launch group.  Semantically identical to n calls of
+ * effort_expert_mul in order.
+ */
+typedef struct {
+    const float* v_dev;
+    const effort_weights_t* w;
+    const uint32_t* exp_no_dev;
+    float* out_dev;
+    double effort;
+} effort_mul_args_t;
+int effort_expert_mul_batch(effort_ctx_t* ctx, const effort_mul_args_t* args, int n, void* stream);
+
+/* ---- test hooks (kept callable "for testing", bucketMul.swift:17) ------- */
+/* BucketMul.calcDispatch  bucketMul.swift:34-48: findCutoff32 + prepareDispatch into ctx scratch
+ * (reference dispatch format: float2 {v, float(rowOffset)}; here in ascending row order), then the
+ * roundUp/zeroRange32 padding of fullMul (bucketMul.swift:57-58). Works for both kinds. */
+int effort_calc_dispatch(effort_ctx_t* ctx, const float* v_dev, const effort_weights_t* w,
+                         const uint32_t* exp_no_dev, double effort, void* stream);
+/* BucketMul.mul  bucketMul.swift:69-88: MAC over the ctx dispatch list + integrate (FP16: overwrites
+ * out; Q4: accumulates into out). */
+int effort_mul(effort_ctx_t* ctx, const effort_weights_t* w, float* out_dev, void* stream);
+/* findCutoff32 only (bucketMul.metal:141-247); result stays in ctx scratch */
+int effort_find_cutoff(effort_ctx_t* ctx, const float* v_dev, const effort_weights_t* w,
+                       const uint32_t* exp_no_dev, double effort, void* stream);
+/* Synchronising reads of ctx scratch (host pointers).  n_selected = rows selected before padding,
+ * padded_size = dispatch.size after roundUp. dispatch_host may be NULL; else it must hold
+ * 2*capacity floats and receives min(padded_size, capacity) entries. */
+int effort_read_dispatch(effort_ctx_t* ctx, float* dispatch_host, size_t capacity, uint32_t* n_selected,
+                         uint32_t* padded_size, float* cutoff, int* cutoff_loops, void* stream);
+
+/* ---- convert ------------------------------------------------------------ */
+/*
+ * bucketize(_:outTensorsPref:tensors:)  convert.swift:209-260 (goQ8 = false): w_dev [out,in] f16 ->
+ * buckets [in*16, out/16] f16, stats [in*16, 4] f16, probes [4096] f16, byte-identical to the
+ * reference layout.  Preconditions of convert.swift:210-215 are returned as EFFORT_EINVAL.
+ */
+int effort_bucketize(const void* w_dev, int out_dim, int in_dim, void* buckets_dev, void* stats_dev,
+                     void* probes_dev, void* stream);
+/*
+ * Q4 convert(core2)  q4_draft.py:70-322 after outlier extraction: wT_dev is W^T [in,out] f16 with the
+ * outliers already zeroed (outlier selection is a global top-2% sort done once on the host side, see
+ * effort_b200/convert.py) -> buckets [in*8, out/32] u16, stats [in*8, 2] f32, probes [min(in,out)] f16.
+ */
+int effort_q4_bucketize(const void* wT_dev, int in_dim, int out_dim, void* buckets_dev, void* stats_dev,
+                        void* probes_dev, void* stream);
+
+/* ---- introspection used by bench / tests -------------------------------- */
+/* number of kernels this library has launched since load (process-wide) */
+uint64_t effort_launch_count(void);
+/* rows selected by the last fused bucket_mul on this ctx (synchronises `stream`) */
+int effort_last_selected(effort_ctx_t* ctx, uint32_t* n_selected, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EFFORT_B200_H */
