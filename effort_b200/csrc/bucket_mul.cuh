@@ -71,60 +71,101 @@ __host__ __device__ inline TileGeom make_geom(int C) {
     return g;
 }
 
-// ---- per-word accumulate ---------------------------------------------------------------------------
+// ---- shared-memory accumulate ---------------------------------------------------------------------
+// A warp tile is SLOTS x (32*VEC) floats, aligned to its own size, laid out [slot][k][lane]:
+//   byte address = tile_base | slot * (128*VEC) | k*128 | lane*4
+// so the slot lands in its own bit field and the whole address is ONE LOP3 ((x & mask) | base_lane)
+// plus an immediate; lane L always hits bank L (conflict free for any slot pattern) and owns its
+// words exclusively (plain read-modify-write, no atomics).
+template <int IMM>
+__device__ __forceinline__ float lds_imm(uint32_t addr) {
+    float x;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(x) : "r"(addr), "n"(IMM));
+    return x;
+}
+template <int IMM>
+__device__ __forceinline__ void sts_imm(uint32_t addr, float x) {
+    asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(addr), "n"(IMM), "f"(x));
+}
+
+template <int VEC>
+struct TileBits {
+    static constexpr int kSlotShift = (VEC == 8) ? 10 : (VEC == 4) ? 9 : 8;  // log2(128*VEC)
+};
+
 // FP16 (SLOTS = 16): out[c*16 + (bits&15)] += val * float(w)       bucketMul.metal:100-106
-// Q4   (SLOTS = 32): for i=3..0: out[c*32 + i*8 + (w&7)] += (w&8) ? -val : val; w >>= 4
+template <int VEC, int J>
+struct AccFp16 {
+    static __device__ __forceinline__ void addr(const uint32_t (&words)[VEC / 2], uint32_t base_lane,
+                                                uint32_t (&a)[VEC], float (&w)[VEC]) {
+        constexpr int SH = TileBits<VEC>::kSlotShift;
+        constexpr uint32_t MASK = 15u << SH;
+        const uint32_t r = words[J];
+        a[2 * J] = ((r << SH) & MASK) | base_lane;
+        a[2 * J + 1] = ((r >> (16 - SH)) & MASK) | base_lane;
+        const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&r));
+        w[2 * J] = f2.x;
+        w[2 * J + 1] = f2.y;
+        if constexpr (J + 1 < VEC / 2) AccFp16<VEC, J + 1>::addr(words, base_lane, a, w);
+    }
+};
+template <int VEC, int K>
+struct RmwFp16 {
+    static __device__ __forceinline__ void load(const uint32_t (&a)[VEC], float (&acc)[VEC]) {
+        acc[K] = lds_imm<K * 128>(a[K]);
+        if constexpr (K + 1 < VEC) RmwFp16<VEC, K + 1>::load(a, acc);
+    }
+    static __device__ __forceinline__ void store(const uint32_t (&a)[VEC], const float (&acc)[VEC]) {
+        sts_imm<K * 128>(a[K], acc[K]);
+        if constexpr (K + 1 < VEC) RmwFp16<VEC, K + 1>::store(a, acc);
+    }
+};
+
+// Q4 (SLOTS = 32): word k, nibble i (low nibble <-> i=3): out[c*32 + i*8 + (w&7)] += (w&8) ? -val : val
 //                                                                   bucketMulQ4.metal:78-83
+// The 4 nibbles of a word address 4 different 8-slot groups: they never alias.
+template <int VEC, int K>
+struct AccQ4 {
+    static __device__ __forceinline__ void run(const uint32_t (&words)[(VEC + 1) / 2], uint32_t base_lane,
+                                               float val) {
+        constexpr int SH = TileBits<VEC>::kSlotShift;  // slot stride = 128*VEC bytes
+        const uint32_t w = (words[K >> 1] >> ((K & 1) * 16)) & 0xFFFFu;
+        uint32_t a[4];
+        float x[4], acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t nib = (w >> (4 * (3 - i))) & 15u;
+            x[i] = (nib & 8u) ? -val : val;
+            a[i] = (((uint32_t)(i * 8) + (nib & 7u)) << SH) | base_lane;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[i] = lds_imm<K * 128>(a[i]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[i] += x[i];
+#pragma unroll
+        for (int i = 0; i < 4; i++) sts_imm<K * 128>(a[i], acc[i]);
+        if constexpr (K + 1 < VEC) AccQ4<VEC, K + 1>::run(words, base_lane, val);
+    }
+};
+
 template <int SLOTS, int VEC>
-__device__ __forceinline__ void accumulate_words(float* __restrict__ tile, int lane, float val,
-                                                 const uint32_t (&words)[VEC / 2]) {
-    constexpr int TW = 32 * VEC;
+__device__ __forceinline__ void accumulate_words(uint32_t base_lane, float val,
+                                                 const uint32_t (&words)[(VEC + 1) / 2]) {
     if constexpr (SLOTS == 16) {
-        float a[VEC];
-        int idx[VEC];
-        float w[VEC];
+        uint32_t a[VEC];
+        float w[VEC], acc[VEC];
+        AccFp16<VEC, 0>::addr(words, base_lane, a, w);
+        RmwFp16<VEC, 0>::load(a, acc);
 #pragma unroll
-        for (int j = 0; j < VEC / 2; j++) {
-            const uint32_t r = words[j];
-            const __half2 h2 = *reinterpret_cast<const __half2*>(&r);
-            const float2 f2 = __half22float2(h2);
-            w[2 * j] = f2.x;
-            w[2 * j + 1] = f2.y;
-            idx[2 * j] = (int)(r & 15u) * TW + (2 * j) * 32 + lane;
-            idx[2 * j + 1] = (int)((r >> 16) & 15u) * TW + (2 * j + 1) * 32 + lane;
-        }
-#pragma unroll
-        for (int k = 0; k < VEC; k++) a[k] = tile[idx[k]];
-#pragma unroll
-        for (int k = 0; k < VEC; k++) a[k] = fmaf(val, w[k], a[k]);
-#pragma unroll
-        for (int k = 0; k < VEC; k++) tile[idx[k]] = a[k];
+        for (int k = 0; k < VEC; k++) acc[k] = fmaf(val, w[k], acc[k]);
+        RmwFp16<VEC, 0>::store(a, acc);
     } else {
-        // one 16-bit word = 4 nibbles that belong to 4 different 8-output groups: never alias
-#pragma unroll
-        for (int k = 0; k < VEC; k++) {
-            uint32_t w = (words[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
-            float a[4];
-            int idx[4];
-            float x[4];
-#pragma unroll
-            for (int i = 3; i >= 0; i--) {
-                x[i] = (w & 8u) ? -val : val;
-                idx[i] = (i * 8 + (int)(w & 7u)) * TW + k * 32 + lane;
-                w >>= 4;
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++) a[i] = tile[idx[i]];
-#pragma unroll
-            for (int i = 0; i < 4; i++) a[i] += x[i];
-#pragma unroll
-            for (int i = 0; i < 4; i++) tile[idx[i]] = a[i];
-        }
+        AccQ4<VEC, 0>::run(words, base_lane, val);
     }
 }
 
 template <int VEC>
-__device__ __forceinline__ void load_words(const uint16_t* p, uint32_t (&words)[VEC / 2]) {
+__device__ __forceinline__ void load_words(const uint16_t* p, uint32_t (&words)[(VEC + 1) / 2]) {
     if constexpr (VEC == 8) {
         uint4 d = ldg_stream_u4(p);
         words[0] = d.x; words[1] = d.y; words[2] = d.z; words[3] = d.w;
@@ -132,44 +173,47 @@ __device__ __forceinline__ void load_words(const uint16_t* p, uint32_t (&words)[
         uint2 d = ldg_stream_u2(p);
         words[0] = d.x; words[1] = d.y;
     } else {
-        words[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+        words[0] = ldg_stream_u1(p);
     }
 }
 
 // ---- streaming: one warp walks its share of the row list --------------------------------------------
+// list entries are {float val, uint32 rowOffset} read with one 8-byte broadcast LDS.  The loop is branch
+// free: an entry past the end (or a lane past the last column) loads nothing and adds 0.0 into the
+// lane's own words.
 template <int SLOTS, int VEC, int U>
-__device__ __forceinline__ void stream_rows(const float* __restrict__ list_val,
-                                            const uint32_t* __restrict__ list_off, int n_list,
+__device__ __forceinline__ void stream_rows(const uint2* __restrict__ list, int n_list,
                                             const uint16_t* __restrict__ bk, int C, const TileGeom g,
-                                            float* __restrict__ tile) {
+                                            uint32_t tile_saddr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = warp % g.CT, s = warp / g.CT;
     if (s >= g.S) return;  // spare warps when kMulWarps % CT != 0
     const int rowslot = lane / g.lanes_per_row;
     const int col = t * 32 * VEC + (lane % g.lanes_per_row) * VEC;
     const bool lane_on = (col < C) && (rowslot < g.R);
+    const uint32_t base_lane = tile_saddr | (uint32_t)(lane * 4);
+    const uint16_t* bk_col = bk + col;
     const int stride = g.S * g.R;  // list entries consumed per step by all streams
     const int first = s * g.R + rowslot;
     const int nsteps = (n_list + stride - 1) / stride;
     for (int n0 = 0; n0 < nsteps; n0 += U) {
-        uint32_t words[U][VEC / 2];
+        uint32_t words[U][(VEC + 1) / 2];
         float val[U];
-        bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int e = (n0 + u) * stride + first;
-            ok[u] = lane_on && (e < n_list);
+            const bool ok = lane_on && (e < n_list);
             val[u] = 0.f;
 #pragma unroll
-            for (int j = 0; j < VEC / 2; j++) words[u][j] = 0u;
-            if (ok[u]) {
-                val[u] = list_val[e];
-                load_words<VEC>(bk + (size_t)list_off[e] + col, words[u]);
+            for (int j = 0; j < (VEC + 1) / 2; j++) words[u][j] = 0u;
+            if (ok) {
+                const uint2 ent = list[e];
+                val[u] = __uint_as_float(ent.x);
+                load_words<VEC>(bk_col + (size_t)ent.y, words[u]);
             }
         }
 #pragma unroll
-        for (int u = 0; u < U; u++)
-            if (ok[u]) accumulate_words<SLOTS, VEC>(tile, lane, val[u], words[u]);
+        for (int u = 0; u < U; u++) accumulate_words<SLOTS, VEC>(base_lane, val[u], words[u]);
     }
 }
 
@@ -197,15 +241,44 @@ __device__ __forceinline__ void reduce_tiles_to_partial(const float* __restrict_
 struct MulSmemHeader {
     CutoffSmem cut;
     int warp_cnt[kMulWarps];
-    int n_list;
-    float cutoff;
 };
 
-// dynamic smem layout: [MulSmemHeader][list_val: cap floats][list_off: cap u32][tiles: kMulWarps*TILE_FLOATS]
+// dynamic smem layout (tiles first, each aligned to its own size so that slot bits can be OR-ed in):
+//   [pad to TILE_BYTES][tiles: kMulWarps*TILE_BYTES][MulSmemHeader][list: cap x uint2]
 template <int SLOTS, int VEC>
-__host__ __device__ inline size_t mul_smem_bytes(int list_cap) {
-    size_t hdr = (sizeof(MulSmemHeader) + 15) & ~size_t(15);
-    return hdr + (size_t)list_cap * 8 + (size_t)kMulWarps * SLOTS * 32 * VEC * 4;
+struct MulSmem {
+    static constexpr int kTileFloats = SLOTS * 32 * VEC;
+    static constexpr int kTileBytes = kTileFloats * 4;
+    static constexpr size_t kHdrBytes = (sizeof(MulSmemHeader) + 15) & ~size_t(15);
+    static __host__ __device__ size_t bytes(int list_cap) {
+        return (size_t)kTileBytes /*alignment slack*/ + (size_t)kMulWarps * kTileBytes + kHdrBytes +
+               (size_t)list_cap * 8;
+    }
+};
+
+template <int SLOTS, int VEC>
+__host__ __device__ inline size_t mul_smem_bytes(int list_cap) { return MulSmem<SLOTS, VEC>::bytes(list_cap); }
+
+struct MulSmemView {
+    float* tiles;          // generic pointer to tile 0
+    uint32_t tiles_saddr;  // shared-window address of tile 0 (aligned to the tile size)
+    MulSmemHeader* hdr;
+    uint2* list;
+};
+
+template <int SLOTS, int VEC>
+__device__ __forceinline__ MulSmemView carve_smem(unsigned char* raw) {
+    using L = MulSmem<SLOTS, VEC>;
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(raw);
+    const uint32_t s1 = (s0 + (uint32_t)L::kTileBytes - 1u) & ~((uint32_t)L::kTileBytes - 1u);
+    unsigned char* p = raw + (s1 - s0);
+    MulSmemView v;
+    v.tiles = reinterpret_cast<float*>(p);
+    v.tiles_saddr = s1;
+    p += (size_t)kMulWarps * L::kTileBytes;
+    v.hdr = reinterpret_cast<MulSmemHeader*>(p);
+    v.list = reinterpret_cast<uint2*>(p + L::kHdrBytes);
+    return v;
 }
 
 // ---- fused kernel: cutoff (optional) + selection + gather-MAC + CTA partial -------------------------
@@ -213,12 +286,10 @@ template <int SLOTS, int VEC, int U>
 __global__ void __launch_bounds__(kMulThreads, 1)
 bucket_mul_fused_kernel(const MulProblem pb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    MulSmemHeader& hdr = *reinterpret_cast<MulSmemHeader*>(smem_raw);
-    const size_t hdr_bytes = (sizeof(MulSmemHeader) + 15) & ~size_t(15);
-    float* list_val = reinterpret_cast<float*>(smem_raw + hdr_bytes);
-    uint32_t* list_off = reinterpret_cast<uint32_t*>(list_val + pb.list_cap);
-    float* tiles = reinterpret_cast<float*>(list_off + pb.list_cap);
-    constexpr int TILE_FLOATS = SLOTS * 32 * VEC;
+    using L = MulSmem<SLOTS, VEC>;
+    const MulSmemView sv = carve_smem<SLOTS, VEC>(smem_raw);
+    MulSmemHeader& hdr = *sv.hdr;
+    uint2* list = sv.list;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t e_no = pb.exp_no ? *pb.exp_no : 0u;
@@ -226,8 +297,8 @@ bucket_mul_fused_kernel(const MulProblem pb) {
 
     // zero this warp's accumulator tile (independent of everything else: overlaps the loads below)
     {
-        float4* t4 = reinterpret_cast<float4*>(tiles + (size_t)warp * TILE_FLOATS);
-        for (int i = lane; i < TILE_FLOATS / 4; i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4* t4 = reinterpret_cast<float4*>(sv.tiles + (size_t)warp * L::kTileFloats);
+        for (int i = lane; i < L::kTileFloats / 4; i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 
     // 1. cutoff
@@ -278,8 +349,7 @@ bucket_mul_fused_kernel(const MulProblem pb) {
         }
         if (sel) {
             const int pos = base + pre + __popc(m & ((1u << lane) - 1u));
-            list_val[pos] = val;
-            list_off[pos] = off;
+            list[pos] = make_uint2(__float_as_uint(val), off);
         }
         base += tot;
         __syncthreads();
@@ -289,12 +359,11 @@ bucket_mul_fused_kernel(const MulProblem pb) {
     __syncthreads();  // list + zeroed tiles visible
 
     // 3. stream the selected rows
-    stream_rows<SLOTS, VEC, U>(list_val, list_off, n_list, pb.bk, pb.C, g,
-                               tiles + (size_t)warp * TILE_FLOATS);
+    stream_rows<SLOTS, VEC, U>(list, n_list, pb.bk, pb.C, g, sv.tiles_saddr + (uint32_t)warp * L::kTileBytes);
     __syncthreads();
 
     // 4. CTA partial
-    reduce_tiles_to_partial<SLOTS, VEC>(tiles, pb.C, g, pb.partial + (size_t)blockIdx.x * pb.C * SLOTS);
+    reduce_tiles_to_partial<SLOTS, VEC>(sv.tiles, pb.C, g, pb.partial + (size_t)blockIdx.x * pb.C * SLOTS);
 }
 
 // ---- test-hook kernel: MAC over a reference-format dispatch list (BucketMul.mul) --------------------
@@ -305,15 +374,13 @@ bucket_mul_dispatch_kernel(const uint16_t* __restrict__ bk, const float2* __rest
                            const uint32_t* __restrict__ dispatch_size, int C, int list_cap,
                            float* __restrict__ partial) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const size_t hdr_bytes = (sizeof(MulSmemHeader) + 15) & ~size_t(15);
-    float* list_val = reinterpret_cast<float*>(smem_raw + hdr_bytes);
-    uint32_t* list_off = reinterpret_cast<uint32_t*>(list_val + list_cap);
-    float* tiles = reinterpret_cast<float*>(list_off + list_cap);
-    constexpr int TILE_FLOATS = SLOTS * 32 * VEC;
+    using L = MulSmem<SLOTS, VEC>;
+    const MulSmemView sv = carve_smem<SLOTS, VEC>(smem_raw);
+    uint2* list = sv.list;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TileGeom g = make_geom<VEC>(C);
-    float4* t4 = reinterpret_cast<float4*>(tiles + (size_t)warp * TILE_FLOATS);
-    for (int i = lane; i < TILE_FLOATS / 4; i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* t4 = reinterpret_cast<float4*>(sv.tiles + (size_t)warp * L::kTileFloats);
+    for (int i = lane; i < L::kTileFloats / 4; i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     // the reference splits the (padded) dispatch into 32 contiguous group slices (bucketMul.metal:94);
     // here: contiguous slices per CTA, walked in chunks of list_cap entries.
@@ -325,14 +392,13 @@ bucket_mul_dispatch_kernel(const uint16_t* __restrict__ bk, const float2* __rest
         __syncthreads();
         for (int i = tid; i < m; i += kMulThreads) {
             const float2 d = dispatch[c0 + i];
-            list_val[i] = d.x;
-            list_off[i] = (uint32_t)d.y;  // int(d[1]), bucketMul.metal:98
+            list[i] = make_uint2(__float_as_uint(d.x), (uint32_t)d.y);  // int(d[1]), bucketMul.metal:98
         }
         __syncthreads();
-        stream_rows<SLOTS, VEC, U>(list_val, list_off, m, bk, C, g, tiles + (size_t)warp * TILE_FLOATS);
+        stream_rows<SLOTS, VEC, U>(list, m, bk, C, g, sv.tiles_saddr + (uint32_t)warp * L::kTileBytes);
     }
     __syncthreads();
-    reduce_tiles_to_partial<SLOTS, VEC>(tiles, C, g, partial + (size_t)blockIdx.x * C * SLOTS);
+    reduce_tiles_to_partial<SLOTS, VEC>(sv.tiles, C, g, partial + (size_t)blockIdx.x * C * SLOTS);
 }
 
 // ---- integrate: out[o] (=|+=) sum_g partial[g][o]      (bucketIntegrate, bucketMul.metal:122-137) ---

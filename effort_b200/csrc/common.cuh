@@ -37,6 +37,11 @@ __device__ __forceinline__ uint2 ldg_stream_u2(const void* p) {
                  : "=r"(r.x), "=r"(r.y) : "l"(p));
     return r;
 }
+__device__ __forceinline__ uint32_t ldg_stream_u1(const void* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
