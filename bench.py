@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+    python bench.py --gpus N --steps K --warmup W            (ours; under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  (CPU arm: the oracle port on the host cores)
+
+Workload (config.workload): Mistral-7B FP16 single-stream decode (BASELINE.json configs[1]): 32 layers x
+7 bucketMul GEMVs (4096->4096 x2, 4096->1024 x2, 4096->14336 x2, 14336->4096) + rmsnorm / rope / attention /
+silu / residual + the dense 4096->32000 lm_head, random-initialised weights (no checkpoints offline), one
+token per step, greedy self-feeding.  A step = one token.  value = tokens/s at --effort (default 0.25, the
+north-star operating point); the same run also reports effort 1.0 and 0.5 in `efforts`.
+
+Timing: W warm-up tokens (>= 3), then exactly K tokens between CUDA events on the launching stream with a
+barrier + synchronize on both sides, max over ranks.  Every token streams the selected rows of 14 GB of
+distinct weights (>> 126 MB L2), so no L2 flush is needed between iterations (config.l2).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Mistral-7B decode tok/s @ effort"
+SHAPES_PER_LAYER = [(4096, 4096), (4096, 1024), (4096, 1024), (4096, 4096), (4096, 14336), (4096, 14336), (14336, 4096)]
+DENSE_LM_HEAD_BYTES = 32000 * 4096 * 2
+BUCKET_BYTES_PER_TOKEN = 32 * sum(2 * i * o for i, o in SHAPES_PER_LAYER)  # 13.958 GB
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the reference has no CPU implementation (Swift+Metal only) -> the oracle port, all host threads
+# ---------------------------------------------------------------------------------------------------------
+def cpu_layer_sample(effort: float, reps: int = 1, seed: int = 1234):
+    """One transformer layer's 7 GEMVs on the host cores, OpenMP on all of them (oracle port).  Returns a dict:
+    bucketmul_s / dense_s = seconds per layer for the bucketMul port at `effort` and for the dense fp16 GEMV
+    (basicMul, matrix.metal:150-162 -- the dense CPU baseline north_star asks for).  Weights: same synthetic
+    distribution, converted by the oracle."""
+    import numpy as np
+    from oracle import oracle as O
+    from tests.util import make_v, make_w
+    by_shape, dense = {}, {}
+    for k, (i, o) in enumerate(sorted(set(SHAPES_PER_LAYER))):
+        w = make_w(o, i, seed + k)
+        dense[(i, o)] = w
+        by_shape[(i, o)] = O.bucketize(w)
+    vs = {i: make_v(i, 42) for i in (4096, 14336)}
+    outs = {o: np.empty(o, np.float32) for o in (4096, 1024, 14336)}
+    scr = {i: np.empty(2 * 16 * i, np.float32) for i in (4096, 14336)}
+
+    def run_bucket():
+        for (i, o) in SHAPES_PER_LAYER:
+            r = by_shape[(i, o)]
+            O.bucket_mul_mt(vs[i], r["buckets"], r["bucket.stats"], r["probes"], i, o, effort, outs[o], scr[i])
+
+    def run_dense():
+        for (i, o) in SHAPES_PER_LAYER:
+            O.basic_mul_fast(vs[i], dense[(i, o)], outs[o])
+
+    res = {}
+    for name, fn in (("bucketmul_s", run_bucket), ("dense_s", run_dense)):
+        fn()  # warm
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        res[name] = (time.perf_counter() - t0) / reps
+    res["threads"] = O.num_threads()
+    res["sample"] = "1 layer (7 GEMVs, 436 MB) x32 = 1 token; lm_head excluded"
+    return res
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    r = cpu_layer_sample(args.effort, reps=max(1, min(steps, 3)))
+    tok_s = 1.0 / (r["bucketmul_s"] * 32)
+    line = {
+        "impl": "reference", "metric": f"{METRIC} {args.effort}", "value": tok_s, "unit": "tok/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": r["bucketmul_s"] * 32 * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "fp16 weights, f32 accumulate", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": tok_s, "unit": "tok/s", "cores": r["threads"], "kind": "port", "sample": r["sample"]},
+        "cpu_dense_gemv": {"value": 1.0 / (r["dense_s"] * 32), "unit": "tok/s", "cores": r["threads"],
+                           "what": "dense fp16 GEMV (basicMul, matrix.metal:150-162) on the same layer sample"},
+        "e2e": {"value": tok_s, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is Swift+Metal (no CPU path, not buildable here): CPU arm = oracle/ port of bucketMul, OpenMP",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "Mistral-7B FP16 single-stream decode, random-init, 32 layers, 1 token/step (BASELINE configs[1])",
+            "effort": args.effort, "context": f"positions {args.warmup}..{args.warmup + args.steps}",
+            "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (TP sharding: round 2)",
+            "l2": "14 GB of distinct weights per token >> 126 MB L2: no flush needed"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ours
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from effort_b200 import ops
+    from effort_b200.model import DecodeModel, MistralConfig
+    from tools.clocks import ClockSampler
+
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        model = DecodeModel.random_init(MistralConfig(n_layers=args.layers), seed=1234 + rank)
+        torch.cuda.synchronize()
+
+        def barrier():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def decode_device(effort, n_warm, n_steps):
+            model.reset()
+            tok = torch.tensor([1], dtype=torch.int32, device="cuda")
+            model.step(tok, effort)
+            for _ in range(max(3, n_warm) - 1):
+                model.step(None, effort)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = ops.launchCount()
+            e0.record(stream)
+            for _ in range(n_steps):
+                model.step(None, effort)
+            e1.record(stream)
+            barrier()
+            ms = e0.elapsed_time(e1)
+            return ms, ops.launchCount() - l0
+
+        # headline: device-resident decode at --effort
+        with ClockSampler(index=local_rank, period=0.02) as cs:
+            ms, launches = decode_device(args.effort, args.warmup, args.steps)
+        clocks = cs.summary()
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tok_s = args.steps * world / (ms / 1e3)
+
+        # end to end: host token in (pinned, H2D), next token + logits out (D2H) every step
+        import numpy as np
+        logits = np.zeros(model.cfg.vocab, np.float32)
+        model.reset()
+        nxt = model.step_host(1, args.effort, logits)
+        for _ in range(max(3, args.warmup) - 1):
+            nxt = model.step_host(nxt, args.effort, logits)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            nxt = model.step_host(nxt, args.effort, logits)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_tok_s = args.steps * world / float(t.item())
+
+        extras = {}
+        if rank == 0 and not args.quick:
+            for eff in (1.0, 0.5):
+                if abs(eff - args.effort) < 1e-9:
+                    continue
+                ms_e, _ = decode_device(eff, 3, max(8, args.steps // 4))
+                extras[str(eff)] = max(8, args.steps // 4) / (ms_e / 1e3)
+        extras[str(args.effort)] = tok_s / world
+
+        # roofline of the dominant operator: bucketMul 4096 -> 14336 (w1/w3; 50 % of the bucket bytes with w2)
+        roof = None
+        if rank == 0:
+            peak, peak_src = peaks()
+            w1s = [L[4] for L in model.layers]            # 32 distinct 117 MB matrices: every launch reads HBM
+            v = torch.randn(4096, device="cuda", dtype=torch.float32)
+            out = torch.empty(14336, device="cuda", dtype=torch.float32)
+            for w in w1s[:4]:
+                ops.bucketMul(v, w, None, out, args.effort)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for w in w1s:
+                    ops.bucketMul(v, w, None, out, args.effort)
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            e0.record(stream)
+            for _ in range(reps):
+                g.replay()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / (reps * len(w1s))
+            alg = args.effort * 4096 * 14336 * 2
+            ach = alg / us / 1e3
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "kernel": "bucketMul 4096->14336 (bucket_mul_fused_kernel + integrate_kernel)",
+                    "us_per_launch": us, "algorithmic_bytes": alg, "peak_source": peak_src}
+
+        cpu = None
+        if rank == 0 and world == 1 and not args.no_cpu:
+            r = cpu_layer_sample(args.effort, reps=1)
+            cpu = {"value": 1.0 / (r["bucketmul_s"] * 32), "unit": "tok/s", "cores": r["threads"], "kind": "port",
+                   "sample": r["sample"], "dense_gemv_tok_s": 1.0 / (r["dense_s"] * 32)}
+
+        if rank == 0:
+            peak, _ = peaks()
+            bytes_tok = args.effort * BUCKET_BYTES_PER_TOKEN * args.layers / 32 + DENSE_LM_HEAD_BYTES
+            line = {
+                "metric": f"{METRIC} {args.effort}", "value": tok_s, "unit": "tok/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "fp16 weights, f32 accumulate",
+                "data": "synthetic", "config": workload_config(args, world),
+                "e2e": {"value": e2e_tok_s, "unit": "tok/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4 + 4 * model.cfg.vocab},
+                "gpu_launches": int(launches),
+                "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
+                "roofline": roof, "cpu_baseline": cpu, "efforts": extras,
+                "token_roofline": {"bytes_per_token": bytes_tok, "tok_s_at_peak": peak * 1e9 / bytes_tok,
+                                   "frac": (tok_s / world) / (peak * 1e9 / bytes_tok)},
+            }
+            print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--effort", type=float, default=0.25)
+    ap.add_argument("--layers", type=int, default=32)
+    ap.add_argument("--quick", action="store_true", help="skip the effort 1.0 / 0.5 extras")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,9 +40,26 @@ SIGNATURES = {
                                        C.POINTER(C.c_float), C.POINTER(C.c_int), vp]),
     "effort_bucketize": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp]),
     "effort_q4_bucketize": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "effort_model_create": (C.c_int, [vp, vp, C.POINTER(C.c_void_p)]),
+    "effort_model_destroy": (C.c_int, [vp]),
+    "effort_model_set_layer": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "effort_model_set_head": (C.c_int, [vp, vp, vp, vp]),
+    "effort_model_reset": (C.c_int, [vp, vp]),
+    "effort_model_step": (C.c_int, [vp, vp, C.c_double, vp]),
+    "effort_model_step_host": (C.c_int, [vp, C.POINTER(C.c_int32), C.c_double, C.POINTER(C.c_int32), vp, vp]),
+    "effort_model_logits": (C.c_void_p, [vp]),
+    "effort_model_next_token": (C.c_void_p, [vp]),
+    "effort_model_bucket_bytes": (C.c_size_t, [vp]),
+    "effort_model_set_graphs": (C.c_int, [vp, C.c_int]),
     "effort_launch_count": (C.c_uint64, []),
     "effort_last_selected": (C.c_int, [vp, C.POINTER(C.c_uint32), vp]),
 }
+
+
+class ModelConfig(C.Structure):
+    _fields_ = [("dim", C.c_int), ("hidden_dim", C.c_int), ("n_layers", C.c_int), ("n_heads", C.c_int),
+                ("n_kv_heads", C.c_int), ("head_dim", C.c_int), ("vocab", C.c_int), ("max_seq", C.c_int),
+                ("rope_theta", C.c_float), ("norm_eps", C.c_float), ("tp_rank", C.c_int), ("tp_size", C.c_int)]
 
 
 class EffortError(RuntimeError):

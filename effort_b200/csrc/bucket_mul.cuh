@@ -11,27 +11,50 @@
 //    weight (ALU bound at 50-70% of DRAM bandwidth, docs/gpu.html:183-187).  Here every WARP owns a
 //    private tile of fp32 accumulators in shared memory laid out [slot][k][lane], so that the
 //    read-modify-write of lane L always hits bank L: conflict free for any slot pattern, and -- because
-//    a lane owns its columns exclusively -- needs no atomics.
-//  * Warps are independent streams: no block barrier inside the streaming loop.  Each lane keeps U
-//    vector loads (8 or 16 bytes, L1::no_allocate) in flight.
-//  * Selection is fused: every CTA tests the stats of the input dims dealt to it (round robin, so the
-//    rank-major concentration of selected rows cannot unbalance CTAs), compacts (val,rowOffset) into a
+//    a lane owns its columns exclusively -- needs no atomics.  6 instructions per weight.
+//  * Decomposition: the C columns are cut into CS slices of 32*VEC columns; the grid is CS x RS CTAs.
+//    CTA (slice, rs) owns one column slice and the input dims i = rs (mod RS) (round robin, so the
+//    concentration of selected rows in the low ranks cannot unbalance CTAs).  All NW warps of the CTA
+//    are independent row streams over the same slice: no block barrier inside the streaming loop, each
+//    lane keeps U vector loads (8 or 16 bytes, L1::no_allocate) in flight.
+//  * Selection is fused: the CTA tests the stats of its input dims, compacts {val,rowOffset} into a
 //    shared-memory list with ballot + prefix scan (deterministic order, no global atomics, no global
 //    dispatch list) and streams only those rows.
-//  * Cross-CTA reduction: CTA partial vectors + a tiny integrate kernel (deterministic).
+//  * Cross-CTA reduction: RS partial tiles per slice (kept in tile layout so that every write and read
+//    is coalesced) + a small integrate kernel that un-permutes into `out` (deterministic order).
 #pragma once
 #include "common.cuh"
 #include "cutoff.cuh"
 
 namespace effort {
 
-constexpr int kMulThreads = 512;  // 16 warps
-constexpr int kMulWarps = kMulThreads / 32;
-
 enum RowLayout : int {
     kInputMajor = 0,  // row(e,i,rho) = (e*in + i)*P + rho      (device repack; Q4 native order)
     kRankMajor = 1,   // row(e,i,rho) = e*P*in + rho*in + i      (reference FP16 order, convert.metal:96)
 };
+
+struct MulGeom {
+    int CS;   // column slices (= tiles of 32*VEC columns)
+    int RS;   // row splits; grid = CS*RS
+    int R;    // rows a warp processes per step (sub-warp rows when C is small)
+    int lpr;  // lanes covering one row inside the tile when R > 1 (else 32)
+};
+
+template <int VEC>
+__host__ __device__ inline MulGeom make_geom(int C, int n_cta) {
+    MulGeom g;
+    const int TW = 32 * VEC;
+    g.CS = (C + TW - 1) / TW;
+    g.RS = n_cta / g.CS;
+    if (g.RS < 1) g.RS = 1;
+    g.R = 1;
+    g.lpr = 32;
+    if (g.CS == 1) {
+        const int lpr = (C + VEC - 1) / VEC;
+        if (lpr <= 16 && (32 % lpr) == 0) { g.R = 32 / lpr; g.lpr = lpr; }
+    }
+    return g;
+}
 
 struct MulProblem {
     const float* v;           // [in] fp32
@@ -41,35 +64,24 @@ struct MulProblem {
     const __half* probes;     // [E][n_probes]
     const uint32_t* exp_no;   // device scalar or null
     const float* cutoff_in;   // precomputed cutoff (device) or null -> computed in-kernel
-    float* partial;           // [gridDim.x][out]
-    uint32_t* sel_counts;     // [gridDim.x] rows selected per CTA
+    float* partial;           // [RS][CS][TILE_FLOATS] in tile layout
+    uint32_t* sel_counts;     // [RS] rows selected per row split (written by slice 0)
     float* cutoff_out;        // optional: CTA 0 stores the cutoff it used
     int in, C, P, n_probes, q, layout;
     int list_cap;             // capacity of the shared-memory row list (entries)
+    MulGeom g;
+    unsigned long long* trace;  // optional [grid][8] phase timestamps (globaltimer ns), debugging aid
 };
 
-struct TileGeom {
-    int CT;             // column tiles per row
-    int S;              // row streams per CTA
-    int R;              // rows a warp processes per step (sub-warp rows when C is small)
-    int lanes_per_row;  // lanes covering one row inside a tile when R > 1 (else 32)
-};
-
-template <int VEC>
-__host__ __device__ inline TileGeom make_geom(int C) {
-    TileGeom g;
-    const int TW = 32 * VEC;
-    g.CT = (C + TW - 1) / TW;
-    if (g.CT > kMulWarps) g.CT = kMulWarps;  // guarded on the host (ESHAPE)
-    g.S = kMulWarps / g.CT;
-    g.R = 1;
-    g.lanes_per_row = 32;
-    if (g.CT == 1) {
-        int lpr = (C + VEC - 1) / VEC;
-        if (lpr <= 16 && (32 % lpr) == 0) { g.R = 32 / lpr; g.lanes_per_row = lpr; }
-    }
-    return g;
+__device__ __forceinline__ unsigned long long gtime_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
+#define EFFORT_TRACE(k)                                                                    \
+    do {                                                                                   \
+        if (pb.trace && threadIdx.x == 0) pb.trace[(size_t)blockIdx.x * 8 + (k)] = gtime_ns(); \
+    } while (0)
 
 // ---- shared-memory accumulate ---------------------------------------------------------------------
 // A warp tile is SLOTS x (32*VEC) floats, aligned to its own size, laid out [slot][k][lane]:
@@ -181,20 +193,18 @@ __device__ __forceinline__ void load_words(const uint16_t* p, uint32_t (&words)[
 // list entries are {float val, uint32 rowOffset} read with one 8-byte broadcast LDS.  The loop is branch
 // free: an entry past the end (or a lane past the last column) loads nothing and adds 0.0 into the
 // lane's own words.
-template <int SLOTS, int VEC, int U>
+template <int SLOTS, int VEC, int U, int NW>
 __device__ __forceinline__ void stream_rows(const uint2* __restrict__ list, int n_list,
-                                            const uint16_t* __restrict__ bk, int C, const TileGeom g,
-                                            uint32_t tile_saddr) {
+                                            const uint16_t* __restrict__ bk, int C, int slice,
+                                            const MulGeom g, uint32_t tile_saddr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t = warp % g.CT, s = warp / g.CT;
-    if (s >= g.S) return;  // spare warps when kMulWarps % CT != 0
-    const int rowslot = lane / g.lanes_per_row;
-    const int col = t * 32 * VEC + (lane % g.lanes_per_row) * VEC;
+    const int rowslot = lane / g.lpr;
+    const int col = slice * 32 * VEC + (lane % g.lpr) * VEC;
     const bool lane_on = (col < C) && (rowslot < g.R);
     const uint32_t base_lane = tile_saddr | (uint32_t)(lane * 4);
     const uint16_t* bk_col = bk + col;
-    const int stride = g.S * g.R;  // list entries consumed per step by all streams
-    const int first = s * g.R + rowslot;
+    const int stride = NW * g.R;  // list entries consumed per step by all warps
+    const int first = warp * g.R + rowslot;
     const int nsteps = (n_list + stride - 1) / stride;
     for (int n0 = 0; n0 < nsteps; n0 += U) {
         uint32_t words[U][(VEC + 1) / 2];
@@ -217,205 +227,322 @@ __device__ __forceinline__ void stream_rows(const uint2* __restrict__ list, int 
     }
 }
 
-// ---- CTA epilogue: fold the warp tiles into one partial vector --------------------------------------
-template <int SLOTS, int VEC>
-__device__ __forceinline__ void reduce_tiles_to_partial(const float* __restrict__ tiles, int C,
-                                                        const TileGeom g, float* __restrict__ partial) {
-    constexpr int TW = 32 * VEC;
-    constexpr int TILE_FLOATS = SLOTS * TW;
-    const int out = C * SLOTS;
-    for (int o = threadIdx.x; o < out; o += blockDim.x) {
-        const int c = o / SLOTS, slot = o % SLOTS;
-        const int t = c / TW, cl = c % TW;
-        const int lane0 = cl / VEC, k = cl % VEC;
-        float sum = 0.f;
-        for (int s = 0; s < g.S; s++) {
-            const float* tile = tiles + (size_t)(s * g.CT + t) * TILE_FLOATS;
-            for (int rs = 0; rs < g.R; rs++)
-                sum += tile[slot * TW + k * 32 + rs * g.lanes_per_row + lane0];
-        }
-        partial[o] = sum;
-    }
-}
-
+template <int NW>
 struct MulSmemHeader {
     CutoffSmem cut;
-    int warp_cnt[kMulWarps];
+    int warp_cnt[NW];
 };
 
 // dynamic smem layout (tiles first, each aligned to its own size so that slot bits can be OR-ed in):
-//   [pad to TILE_BYTES][tiles: kMulWarps*TILE_BYTES][MulSmemHeader][list: cap x uint2]
-template <int SLOTS, int VEC>
+//   [pad to TILE_BYTES][tiles: NW*TILE_BYTES][MulSmemHeader][list: cap x uint2]
+template <int SLOTS, int VEC, int NW>
 struct MulSmem {
     static constexpr int kTileFloats = SLOTS * 32 * VEC;
     static constexpr int kTileBytes = kTileFloats * 4;
-    static constexpr size_t kHdrBytes = (sizeof(MulSmemHeader) + 15) & ~size_t(15);
+    static constexpr size_t kHdrBytes = (sizeof(MulSmemHeader<NW>) + 15) & ~size_t(15);
     static __host__ __device__ size_t bytes(int list_cap) {
-        return (size_t)kTileBytes /*alignment slack*/ + (size_t)kMulWarps * kTileBytes + kHdrBytes +
-               (size_t)list_cap * 8;
+        return (size_t)kTileBytes /*alignment slack*/ + (size_t)NW * kTileBytes + kHdrBytes + (size_t)list_cap * 8;
     }
 };
 
-template <int SLOTS, int VEC>
-__host__ __device__ inline size_t mul_smem_bytes(int list_cap) { return MulSmem<SLOTS, VEC>::bytes(list_cap); }
-
+template <int NW>
 struct MulSmemView {
     float* tiles;          // generic pointer to tile 0
     uint32_t tiles_saddr;  // shared-window address of tile 0 (aligned to the tile size)
-    MulSmemHeader* hdr;
+    MulSmemHeader<NW>* hdr;
     uint2* list;
 };
 
-template <int SLOTS, int VEC>
-__device__ __forceinline__ MulSmemView carve_smem(unsigned char* raw) {
-    using L = MulSmem<SLOTS, VEC>;
+template <int SLOTS, int VEC, int NW>
+__device__ __forceinline__ MulSmemView<NW> carve_smem(unsigned char* raw) {
+    using L = MulSmem<SLOTS, VEC, NW>;
     const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(raw);
     const uint32_t s1 = (s0 + (uint32_t)L::kTileBytes - 1u) & ~((uint32_t)L::kTileBytes - 1u);
     unsigned char* p = raw + (s1 - s0);
-    MulSmemView v;
+    MulSmemView<NW> v;
     v.tiles = reinterpret_cast<float*>(p);
     v.tiles_saddr = s1;
-    p += (size_t)kMulWarps * L::kTileBytes;
-    v.hdr = reinterpret_cast<MulSmemHeader*>(p);
+    p += (size_t)NW * L::kTileBytes;
+    v.hdr = reinterpret_cast<MulSmemHeader<NW>*>(p);
     v.list = reinterpret_cast<uint2*>(p + L::kHdrBytes);
     return v;
 }
 
+template <int SLOTS, int VEC, int NW>
+__device__ __forceinline__ void zero_my_tile(float* tiles) {
+    constexpr int TF = MulSmem<SLOTS, VEC, NW>::kTileFloats;
+    float4* t4 = reinterpret_cast<float4*>(tiles + (size_t)(threadIdx.x >> 5) * TF);
+    for (int i = threadIdx.x & 31; i < TF / 4; i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// ---- CTA epilogue: fold the NW warp tiles (and the R row slots) into one partial tile ----------------
+// Thread t handles tile words t, t+NT, ...: consecutive lanes read consecutive banks and the global write
+// is coalesced.  Lanes >= lpr of a sub-warp-row tile are folded into lane % lpr and written as 0.
+template <int SLOTS, int VEC, int NW>
+__device__ __forceinline__ void reduce_tiles_to_partial(const float* __restrict__ tiles, const MulGeom g,
+                                                        float* __restrict__ partial) {
+    constexpr int TF = MulSmem<SLOTS, VEC, NW>::kTileFloats;
+    for (int idx = threadIdx.x; idx < TF; idx += NW * 32) {
+        const int lane = idx & 31;
+        float sum = 0.f;
+        if (lane < g.lpr) {
+            for (int rs = 0; rs < g.R; rs++)
+#pragma unroll
+                for (int w = 0; w < NW; w++) sum += tiles[(size_t)w * TF + idx + rs * g.lpr];
+        }
+        partial[idx] = sum;
+    }
+}
+
 // ---- fused kernel: cutoff (optional) + selection + gather-MAC + CTA partial -------------------------
-template <int SLOTS, int VEC, int U>
-__global__ void __launch_bounds__(kMulThreads, 1)
+template <int SLOTS, int VEC, int U, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
 bucket_mul_fused_kernel(const MulProblem pb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    using L = MulSmem<SLOTS, VEC>;
-    const MulSmemView sv = carve_smem<SLOTS, VEC>(smem_raw);
-    MulSmemHeader& hdr = *sv.hdr;
+    using L = MulSmem<SLOTS, VEC, NW>;
+    constexpr int NT = NW * 32;
+    const MulSmemView<NW> sv = carve_smem<SLOTS, VEC, NW>(smem_raw);
+    MulSmemHeader<NW>& hdr = *sv.hdr;
     uint2* list = sv.list;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t e_no = pb.exp_no ? *pb.exp_no : 0u;
-    const TileGeom g = make_geom<VEC>(pb.C);
+    const MulGeom g = pb.g;
+    const int slice = (int)blockIdx.x % g.CS, rsp = (int)blockIdx.x / g.CS;
 
-    // zero this warp's accumulator tile (independent of everything else: overlaps the loads below)
-    {
-        float4* t4 = reinterpret_cast<float4*>(sv.tiles + (size_t)warp * L::kTileFloats);
-        for (int i = lane; i < L::kTileFloats / 4; i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    EFFORT_TRACE(0);
+    zero_my_tile<SLOTS, VEC, NW>(sv.tiles);  // independent of everything else: overlaps the loads below
+
+    // 0. issue every global load the selection needs BEFORE the cutoff is known (they do not depend on
+    //    it): thread <-> input dim i = rsp + j*RS, its v[i] and its P stats (32 contiguous bytes in the
+    //    input-major repack).  One DRAM/L2 round trip for the whole prologue instead of one per stage.
+    const int P = pb.P;
+    const int n_in = (pb.in > rsp) ? (pb.in - 1 - rsp) / g.RS + 1 : 0;
+    constexpr int KSEL = 2;  // inputs per thread held in registers; more are handled by the tail loop
+    float sel_v[KSEL];
+    float sel_stat[KSEL][16];
+#pragma unroll
+    for (int k = 0; k < KSEL; k++) {
+        const int j = tid + k * NT;
+        sel_v[k] = 0.f;
+#pragma unroll
+        for (int rho = 0; rho < 16; rho++) sel_stat[k][rho] = 0.f;
+        if (j < n_in) {
+            const int i = rsp + j * g.RS;
+            sel_v[k] = pb.v[i];
+            if constexpr (SLOTS == 16) {
+                if (pb.layout == kInputMajor && P == 16) {
+                    const uint4* sp = reinterpret_cast<const uint4*>(pb.st16 + ((size_t)e_no * pb.in + i) * 16);
+                    const uint4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+                    const uint32_t ws[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                    for (int q2 = 0; q2 < 8; q2++) {
+                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ws[q2]));
+                        sel_stat[k][2 * q2] = f.x;
+                        sel_stat[k][2 * q2 + 1] = f.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int rho = 0; rho < 16; rho++)
+                        if (rho < P) {
+                            const size_t row = (pb.layout == kInputMajor)
+                                                   ? ((size_t)e_no * pb.in + i) * P + rho
+                                                   : (size_t)e_no * P * pb.in + (size_t)rho * pb.in + i;
+                            sel_stat[k][rho] = __half2float(pb.st16[row]);
+                        }
+                }
+            } else {
+#pragma unroll
+                for (int rho = 0; rho < 16; rho++)
+                    if (rho < P) sel_stat[k][rho] = pb.st32[((size_t)e_no * pb.in + i) * P + rho];
+            }
+        }
     }
 
-    // 1. cutoff
+    // 1. cutoff (every CTA redundantly: 24 KB of L2-resident inputs, no extra launch / global round trip)
     float cutoff;
     if (pb.cutoff_in) {
         cutoff = *pb.cutoff_in;
     } else {
-        float vals[kCutoffMaxPerThread * (kCutoffThreads / kMulThreads)];
+        constexpr int PER = (kCutoffThreads * kCutoffMaxPerThread + NT - 1) / NT;
+        float vals[PER];
         score_probes(pb.v, pb.probes, e_no, pb.n_probes, vals);
+        EFFORT_TRACE(1);
         cutoff = block_bisect_cutoff(vals, pb.n_probes, pb.q, hdr.cut, nullptr);
     }
     if (pb.cutoff_out && blockIdx.x == 0 && tid == 0) *pb.cutoff_out = cutoff;
+    EFFORT_TRACE(2);
 
-    // 2. selection: input dims i = blockIdx.x + j*gridDim.x; thread <-> (j, rho)
-    const int P = pb.P;
-    const int n_in = (pb.in > (int)blockIdx.x) ? (pb.in - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int n_rows = n_in * P;
+    // 2. selection + compaction.  Thread order == (input, rank) order == ascending row order, so the list
+    //    is deterministic and consecutive entries are consecutive rows in HBM.
     int base = 0;
-    for (int r0 = 0; r0 < n_rows; r0 += kMulThreads) {
-        const int r = r0 + tid;
-        bool sel = false;
-        float val = 0.f;
-        uint32_t off = 0;
-        if (r < n_rows) {
-            const int j = r / P, rho = r % P;
-            const int i = (int)blockIdx.x + j * (int)gridDim.x;
-            const size_t row = (pb.layout == kInputMajor)
-                                   ? ((size_t)e_no * pb.in + i) * P + rho
-                                   : (size_t)e_no * P * pb.in + (size_t)rho * pb.in + i;
-            const float vi = pb.v[i];
-            float stat;
-            if constexpr (SLOTS == 16) stat = __half2float(pb.st16[row]);
-            else stat = pb.st32[row];
-            sel = row_selected(cutoff, stat, vi);
-            // Q4 payload is v*avg (bucketMulQ4.metal:51)
-            val = (SLOTS == 16) ? vi : __fmul_rn(vi, stat);
-            off = (uint32_t)(row * (size_t)pb.C);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, sel);
-        if (lane == 0) hdr.warp_cnt[warp] = __popc(m);
-        __syncthreads();
-        int pre = 0, tot = 0;
+    for (int j0 = 0; j0 < n_in; j0 += NT * KSEL) {
+        unsigned mask[KSEL];
+        int cnt = 0;
 #pragma unroll
-        for (int w = 0; w < kMulWarps; w++) {
-            const int c = hdr.warp_cnt[w];
-            pre += (w < warp) ? c : 0;
-            tot += c;
+        for (int k = 0; k < KSEL; k++) {
+            mask[k] = 0u;
+            const int j = j0 + tid + k * NT;
+            if (j0 == 0) {
+#pragma unroll
+                for (int rho = 0; rho < 16; rho++)
+                    if (rho < P && j < n_in && row_selected(cutoff, sel_stat[k][rho], sel_v[k])) mask[k] |= 1u << rho;
+            } else if (j < n_in) {  // tail (more than NT*KSEL inputs per CTA): loads not prefetched
+                const int i = rsp + j * g.RS;
+                sel_v[k] = pb.v[i];
+                for (int rho = 0; rho < P; rho++) {
+                    const size_t row = (pb.layout == kInputMajor)
+                                           ? ((size_t)e_no * pb.in + i) * P + rho
+                                           : (size_t)e_no * P * pb.in + (size_t)rho * pb.in + i;
+                    float st;
+                    if constexpr (SLOTS == 16) st = __half2float(pb.st16[row]);
+                    else st = pb.st32[row];
+                    if (row_selected(cutoff, st, sel_v[k])) mask[k] |= 1u << rho;
+                }
+            }
+            cnt += __popc(mask[k]);
         }
-        if (sel) {
-            const int pos = base + pre + __popc(m & ((1u << lane) - 1u));
-            list[pos] = make_uint2(__float_as_uint(val), off);
+        // block exclusive scan of cnt (order: k-major inside a thread is NOT input order, so scan per k)
+#pragma unroll
+        for (int k = 0; k < KSEL; k++) {
+            const int c = __popc(mask[k]);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) hdr.warp_cnt[warp] = incl;
+            __syncthreads();
+            int pre = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                const int wc = hdr.warp_cnt[w];
+                pre += (w < warp) ? wc : 0;
+                tot += wc;
+            }
+            int pos = base + pre + incl - c;
+            const int j = j0 + tid + k * NT;
+            if (c) {
+                const int i = rsp + j * g.RS;
+                unsigned m = mask[k];
+                while (m) {
+                    const int rho = __ffs(m) - 1;
+                    m &= m - 1;
+                    const size_t row = (pb.layout == kInputMajor)
+                                           ? ((size_t)e_no * pb.in + i) * P + rho
+                                           : (size_t)e_no * P * pb.in + (size_t)rho * pb.in + i;
+                    // Q4 payload is v*avg (bucketMulQ4.metal:51)
+                    float val = sel_v[k];
+                    if constexpr (SLOTS != 16) {
+                        float st = 0.f;
+                        if (j0 == 0) {
+#pragma unroll
+                            for (int r2 = 0; r2 < 16; r2++) st = (r2 == rho) ? sel_stat[k][r2] : st;
+                        } else {
+                            st = pb.st32[row];
+                        }
+                        val = __fmul_rn(val, st);
+                    }
+                    list[pos++] = make_uint2(__float_as_uint(val), (uint32_t)(row * (size_t)pb.C));
+                }
+            }
+            base += tot;
+            __syncthreads();
         }
-        base += tot;
-        __syncthreads();
+        (void)cnt;
     }
     const int n_list = base;
-    if (pb.sel_counts && tid == 0) pb.sel_counts[blockIdx.x] = (uint32_t)n_list;
+    if (pb.sel_counts && slice == 0 && tid == 0) pb.sel_counts[rsp] = (uint32_t)n_list;
     __syncthreads();  // list + zeroed tiles visible
+    EFFORT_TRACE(3);
 
     // 3. stream the selected rows
-    stream_rows<SLOTS, VEC, U>(list, n_list, pb.bk, pb.C, g, sv.tiles_saddr + (uint32_t)warp * L::kTileBytes);
+    stream_rows<SLOTS, VEC, U, NW>(list, n_list, pb.bk, pb.C, slice, g,
+                                   sv.tiles_saddr + (uint32_t)warp * L::kTileBytes);
     __syncthreads();
+    EFFORT_TRACE(4);
 
-    // 4. CTA partial
-    reduce_tiles_to_partial<SLOTS, VEC>(sv.tiles, pb.C, g, pb.partial + (size_t)blockIdx.x * pb.C * SLOTS);
+    // 4. CTA partial (tile layout)
+    reduce_tiles_to_partial<SLOTS, VEC, NW>(sv.tiles, g, pb.partial + (size_t)blockIdx.x * L::kTileFloats);
+    EFFORT_TRACE(5);
 }
 
 // ---- test-hook kernel: MAC over a reference-format dispatch list (BucketMul.mul) --------------------
 // dispatch: float2 {val, float(rowOffset)} in the reference's rank-major element offsets.
-template <int SLOTS, int VEC, int U>
-__global__ void __launch_bounds__(kMulThreads, 1)
+template <int SLOTS, int VEC, int U, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
 bucket_mul_dispatch_kernel(const uint16_t* __restrict__ bk, const float2* __restrict__ dispatch,
-                           const uint32_t* __restrict__ dispatch_size, int C, int list_cap,
+                           const uint32_t* __restrict__ dispatch_size, int C, int list_cap, const MulGeom g,
                            float* __restrict__ partial) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    using L = MulSmem<SLOTS, VEC>;
-    const MulSmemView sv = carve_smem<SLOTS, VEC>(smem_raw);
+    using L = MulSmem<SLOTS, VEC, NW>;
+    constexpr int NT = NW * 32;
+    const MulSmemView<NW> sv = carve_smem<SLOTS, VEC, NW>(smem_raw);
     uint2* list = sv.list;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const TileGeom g = make_geom<VEC>(C);
-    float4* t4 = reinterpret_cast<float4*>(sv.tiles + (size_t)warp * L::kTileFloats);
-    for (int i = lane; i < L::kTileFloats / 4; i += 32) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int slice = (int)blockIdx.x % g.CS, rsp = (int)blockIdx.x / g.CS;
+    zero_my_tile<SLOTS, VEC, NW>(sv.tiles);
 
     // the reference splits the (padded) dispatch into 32 contiguous group slices (bucketMul.metal:94);
-    // here: contiguous slices per CTA, walked in chunks of list_cap entries.
+    // here: RS contiguous slices, walked in chunks of list_cap entries.
     const uint32_t n = *dispatch_size;
-    const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
-    const uint32_t lo = min(n, per * blockIdx.x), hi = min(n, lo + per);
+    const uint32_t per = (n + g.RS - 1) / g.RS;
+    const uint32_t lo = min(n, per * (uint32_t)rsp), hi = min(n, lo + per);
     for (uint32_t c0 = lo; c0 < hi; c0 += (uint32_t)list_cap) {
         const int m = (int)min((uint32_t)list_cap, hi - c0);
         __syncthreads();
-        for (int i = tid; i < m; i += kMulThreads) {
+        for (int i = tid; i < m; i += NT) {
             const float2 d = dispatch[c0 + i];
             list[i] = make_uint2(__float_as_uint(d.x), (uint32_t)d.y);  // int(d[1]), bucketMul.metal:98
         }
         __syncthreads();
-        stream_rows<SLOTS, VEC, U>(list, m, bk, C, g, sv.tiles_saddr + (uint32_t)warp * L::kTileBytes);
+        stream_rows<SLOTS, VEC, U, NW>(list, m, bk, C, slice, g, sv.tiles_saddr + (uint32_t)warp * L::kTileBytes);
     }
     __syncthreads();
-    reduce_tiles_to_partial<SLOTS, VEC>(sv.tiles, C, g, partial + (size_t)blockIdx.x * C * SLOTS);
+    reduce_tiles_to_partial<SLOTS, VEC, NW>(sv.tiles, g, partial + (size_t)blockIdx.x * L::kTileFloats);
 }
 
-// ---- integrate: out[o] (=|+=) sum_g partial[g][o]      (bucketIntegrate, bucketMul.metal:122-137) ---
-// accumulate != 0 keeps the Q4 semantics (atomic adds INTO out, bucketMulQ4.metal:89).
+// ---- integrate: out[o] (=|+=) sum over the RS partial tiles   (bucketIntegrate, bucketMul.metal:122-137)
+// Block = 8 warps x 32 consecutive tile words: warp w sums the partials r = w (mod 8) (coalesced 128-byte
+// rows, all loads independent), shared-memory fold, then warp 0 un-permutes tile word -> output index.
+// accumulate != 0 keeps the Q4 semantics (adds INTO out, bucketMulQ4.metal:89).
+template <int SLOTS, int VEC>
 __global__ void __launch_bounds__(256)
-integrate_kernel(const float* __restrict__ partial, int n_partials, int out, int accumulate,
+integrate_kernel(const float* __restrict__ partial, const MulGeom g, int C, int accumulate,
                  float* __restrict__ out_vec, const uint32_t* __restrict__ sel_counts,
                  uint32_t* __restrict__ n_selected) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o < out) {
-        float s = 0.f;
-        for (int gq = 0; gq < n_partials; gq++) s += partial[(size_t)gq * out + o];
-        out_vec[o] = accumulate ? out_vec[o] + s : s;
+    constexpr int TW = 32 * VEC;
+    constexpr int TF = SLOTS * TW;
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane;  // word index in [0, CS*TF)
+    const int slice = j / TF, idx = j % TF;
+    float s = 0.f;
+    if (slice < g.CS) {
+        const float* p = partial + (size_t)slice * TF + idx;
+        const size_t rstride = (size_t)g.CS * TF;
+#pragma unroll 4
+        for (int r = w; r < g.RS; r += 8) s += p[(size_t)r * rstride];
+    }
+    red[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && slice < g.CS) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) t += red[k][lane];
+        const int slot = idx / TW, k = (idx % TW) / 32;
+        if (lane < g.lpr) {
+            const int col = slice * TW + lane * VEC + k;
+            if (col < C) {
+                const int o = col * SLOTS + slot;
+                out_vec[o] = accumulate ? out_vec[o] + t : t;
+            }
+        }
     }
     if (n_selected && sel_counts && blockIdx.x == 0 && threadIdx.x == 0) {
         uint32_t t = 0;
-        for (int gq = 0; gq < n_partials; gq++) t += sel_counts[gq];
+        for (int r = 0; r < g.RS; r++) t += sel_counts[r];
         *n_selected = t;
     }
 }

@@ -1,0 +1,168 @@
+// decode.cuh -- the non-GEMV steps either side of the hot path in the single-stream decode loop
+// (reference: runNetwork.swift:113-209 with kernels from aux.metal / matrix.metal).  These are the "next"
+// rows of the scope table: kept simple and HBM/latency-lean; every
+// approximate GEMV in the loop goes through the bucketMul path.
+#pragma once
+#include "common.cuh"
+
+namespace effort {
+
+// fetchRow16to32 (aux.metal:355-363): x = float(tok_embeddings[token])
+__global__ void embed_kernel(const int* __restrict__ token, const __half* __restrict__ emb, int dim,
+                             float* __restrict__ x) {
+    const int t = *token;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += gridDim.x * blockDim.x)
+        x[i] = __half2float(emb[(size_t)t * dim + i]);
+}
+
+// h (+= add) ; out = rmsNormFast(h) * w     (rmsNorm32fast aux.metal:113-152: x / sqrt(mean(x^2) + 1e-5),
+// then mulVec32by16 aux.metal:269).  One CTA of 1024 threads; `add` may be null.  h is updated in place
+// when add != null (h.add(by:), runNetwork.swift:172,183).
+__global__ void __launch_bounds__(1024)
+add_rmsnorm_kernel(float* __restrict__ h, const float* __restrict__ add, const __half* __restrict__ w,
+                   int dim, float eps, float* __restrict__ out) {
+    __shared__ float red[32];
+    __shared__ float total;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+        float x = h[i];
+        if (add) { x += add[i]; h[i] = x; }
+        ss += x * x;
+    }
+    ss = warp_sum_f(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+        t = warp_sum_f(t);
+        if (threadIdx.x == 0) total = t;
+    }
+    __syncthreads();
+    const float denom = sqrtf(total / (float)dim + eps);
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) out[i] = (h[i] / denom) * __half2float(w[i]);
+}
+
+// h += add (last residual of the token loop, runNetwork.swift:183)
+__global__ void add_kernel(float* __restrict__ h, const float* __restrict__ add, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) h[i] += add[i];
+}
+
+// silu32b (matrix.metal:25-34): out = x3 * x1 / (1 + exp(-x1))
+__global__ void silu_mul_kernel(const float* __restrict__ x1, const float* __restrict__ x3, int n,
+                                float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = x3[i] * x1[i] / (1.f + expf(-x1[i]));
+}
+
+// Attention for one new token (runNetwork.swift:136-164): rope_mx on q and k (aux.metal:218-231, HF
+// rotate-half, theta = 1e6: freqs = 1e-6^(j/64), model.swift:693-717), append k/v to the cache, scores =
+// q.k/sqrt(headDim) (dotSetScore2 aux.metal:397-447), softmax = exp(s)/sum(exp(s)) WITHOUT max subtraction
+// (aux.metal:185-199), out = sum_t p_t * v_t (sumScores32 aux.metal:379-393).
+// The reference materialises K/V repeated x4 for GQA (runNetwork.swift:136-137); here the 8 KV heads are
+// stored once and head h reads KV head h / (n_heads/n_kv_heads) -- same arithmetic, a quarter of the bytes.
+// One CTA per query head, 8 warps striding over the tokens, lane <-> 4 of the 128 head dims.
+// pos is read from device memory so that the whole token can live in one replayable CUDA graph.
+__global__ void __launch_bounds__(256)
+attention_kernel(const float* __restrict__ xq, const float* __restrict__ xk, const float* __restrict__ xv,
+                 float* __restrict__ kcache, float* __restrict__ vcache,  // [max_seq][n_kv][128]
+                 const int* __restrict__ pos_dev, int n_heads, int n_kv, float theta, int tp_head0,
+                 float* __restrict__ attn_out) {
+    constexpr int HD = 128;
+    __shared__ float q[HD];
+    __shared__ float acc_s[8][HD];
+    __shared__ float sum_s[8];
+    const int h = blockIdx.x, kvh = h / (n_heads / n_kv);
+    const int pos = *pos_dev;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    (void)tp_head0;
+    // rope(q) into smem; the first head of each KV group also ropes k and appends k/v to the cache
+    if (tid < HD) {
+        const int j = tid & 63;
+        const float freq = powf(1e-6f * (1e6f / theta), (float)j / 64.f);  // theta=1e6 -> 1e-6^(j/64)
+        const float ang = (float)pos * freq;
+        const float c = cosf(ang), s = sinf(ang);
+        const float* qh = xq + (size_t)h * HD;
+        q[tid] = (tid < 64) ? qh[tid] * c - qh[tid + 64] * s : qh[tid] * c + qh[tid - 64] * s;
+        if (h % (n_heads / n_kv) == 0) {
+            const float* kh = xk + (size_t)kvh * HD;
+            const float kr = (tid < 64) ? kh[tid] * c - kh[tid + 64] * s : kh[tid] * c + kh[tid - 64] * s;
+            kcache[((size_t)pos * n_kv + kvh) * HD + tid] = kr;
+            vcache[((size_t)pos * n_kv + kvh) * HD + tid] = xv[(size_t)kvh * HD + tid];
+        }
+    }
+    __syncthreads();
+    const float4 q4 = *reinterpret_cast<const float4*>(&q[lane * 4]);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sum = 0.f;
+    const float scale = rsqrtf((float)HD);
+    for (int t = warp; t <= pos; t += 8) {
+        float4 k4, v4;
+        if (t == pos) {  // the entry this token appends: written by another CTA of the group, read the source
+            const int j0 = lane * 4;
+            float kk[4];
+#pragma unroll
+            for (int d = 0; d < 4; d++) {
+                const int x = j0 + d, j = x & 63;
+                const float freq = powf(1e-6f * (1e6f / theta), (float)j / 64.f);
+                const float ang = (float)pos * freq;
+                const float c = cosf(ang), s = sinf(ang);
+                const float* kh = xk + (size_t)kvh * HD;
+                kk[d] = (x < 64) ? kh[x] * c - kh[x + 64] * s : kh[x] * c + kh[x - 64] * s;
+            }
+            k4 = make_float4(kk[0], kk[1], kk[2], kk[3]);
+            v4 = *reinterpret_cast<const float4*>(xv + (size_t)kvh * HD + j0);
+        } else {
+            k4 = *reinterpret_cast<const float4*>(kcache + ((size_t)t * n_kv + kvh) * HD + lane * 4);
+            v4 = *reinterpret_cast<const float4*>(vcache + ((size_t)t * n_kv + kvh) * HD + lane * 4);
+        }
+        float d = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
+        d = warp_sum_f(d);
+        const float p = expf(d * scale);
+        sum += p;
+        acc.x += p * v4.x; acc.y += p * v4.y; acc.z += p * v4.z; acc.w += p * v4.w;
+    }
+    *reinterpret_cast<float4*>(&acc_s[warp][lane * 4]) = acc;
+    if (lane == 0) sum_s[warp] = sum;
+    __syncthreads();
+    if (tid < HD) {
+        float a = 0.f, s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { a += acc_s[w][tid]; s += sum_s[w]; }
+        attn_out[(size_t)h * HD + tid] = a / s;
+    }
+}
+
+// greedy next token: argmax over the logits (mpsTopK index 0, runNetwork.swift:235-257); also bumps pos.
+__global__ void __launch_bounds__(1024)
+argmax_advance_kernel(const float* __restrict__ logits, int n, int* __restrict__ next_token,
+                      int* __restrict__ pos_dev) {
+    __shared__ float bv[32];
+    __shared__ int bi[32];
+    float best = -INFINITY;
+    int idx = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float x = logits[i];
+        if (x > best || (x == best && i < idx)) { best = x; idx = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = bv[threadIdx.x]; idx = bi[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+        }
+        if (threadIdx.x == 0) { *next_token = idx; *pos_dev = *pos_dev + 1; }
+    }
+}
+
+}  // namespace effort

@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -46,6 +47,7 @@ struct effort_weights {
     const __half* core = nullptr;
     // owned device copies
     uint16_t* bk_own = nullptr;  // input-major rows (FP16 kind, unless NO_REPACK)
+    __half* probes_own = nullptr;  // copy of the caller's probes (8 KB per expert)
     __half* st16 = nullptr;      // FP16: one stat per row (row order == fast-path bucket order)
     float* st32 = nullptr;       // Q4
     size_t owned = 0;
@@ -71,6 +73,7 @@ struct effort_ctx {
     size_t sel_cap = 0;
     bool have_dispatch = false;
     int dispatch_kind = 0;
+    unsigned long long* trace = nullptr;  // [n_sms][8] when EFFORT_TRACE=1
 };
 
 static constexpr int kMaxBatch = 8;
@@ -113,8 +116,22 @@ extern "C" int effort_ctx_create(int device, effort_ctx_t** ctx_out) {
     CK(cudaMemset(c->sizes, 0, sizeof(uint32_t) * (4 + kMaxBatch)));
     CK(cudaMemset(c->cutoff, 0, sizeof(float) * kMaxBatch));
     CK(cudaMemset(c->loops, 0, sizeof(int)));
+    if (getenv("EFFORT_TRACE")) {
+        CK(cudaMalloc(&c->trace, sizeof(unsigned long long) * 8 * c->n_sms));
+        CK(cudaMemset(c->trace, 0, sizeof(unsigned long long) * 8 * c->n_sms));
+    }
     *ctx_out = c;
     return EFFORT_OK;
+}
+
+// debugging aid (not part of the public header): copies the [n_sms][8] phase timestamps of the last fused
+// launch; returns the number of CTAs rows or <0.
+extern "C" int effort_debug_read_trace(effort_ctx_t* c, unsigned long long* host, int max_rows) {
+    if (!c || !c->trace || !host) return EFFORT_EINVAL;
+    CK(cudaDeviceSynchronize());
+    int n = c->n_sms < max_rows ? c->n_sms : max_rows;
+    CK(cudaMemcpy(host, c->trace, sizeof(unsigned long long) * 8 * n, cudaMemcpyDeviceToHost));
+    return n;
 }
 
 extern "C" int effort_ctx_destroy(effort_ctx_t* c) {
@@ -169,6 +186,11 @@ extern "C" int effort_weights_create(const void* buckets_dev, const void* stats_
         const size_t rows = (size_t)n_experts * in_dim * percent_load;
         if (rows * (size_t)w->C >= (size_t)1 << 32) { delete w; return EFFORT_ESHAPE; }
         const int TB = 256;
+        CK(cudaMalloc(&w->probes_own, (size_t)n_experts * EFFORT_PROBES_COUNT * sizeof(__half)));
+        CK(cudaMemcpyAsync(w->probes_own, probes_dev, (size_t)n_experts * EFFORT_PROBES_COUNT * sizeof(__half),
+                           cudaMemcpyDeviceToDevice, stream));
+        w->probes = w->probes_own;
+        w->owned += (size_t)n_experts * EFFORT_PROBES_COUNT * sizeof(__half);
         if (kind == EFFORT_KIND_FP16) {
             const bool repack = !(flags & EFFORT_WEIGHTS_NO_REPACK);
             w->layout = repack ? kInputMajor : kRankMajor;
@@ -199,7 +221,7 @@ extern "C" int effort_weights_create(const void* buckets_dev, const void* stats_
 
 extern "C" int effort_weights_destroy(effort_weights_t* w) {
     if (!w) return EFFORT_OK;
-    cudaFree(w->bk_own); cudaFree(w->st16); cudaFree(w->st32);
+    cudaFree(w->bk_own); cudaFree(w->st16); cudaFree(w->st32); cudaFree(w->probes_own);
     delete w;
     return EFFORT_OK;
 }
@@ -221,54 +243,80 @@ static int check_mul_args(const effort_ctx* ctx, const float* v, const effort_we
     return EFFORT_OK;
 }
 
-template <int SLOTS, int VEC, int U>
-static int launch_fused(effort_ctx* ctx, const MulProblem& pb, int grid, cudaStream_t stream) {
-    const size_t smem = mul_smem_bytes<SLOTS, VEC>(pb.list_cap);
+// kernel variants (FP16 kind).  EFFORT_MUL_VARIANT selects one at run time for experiments.
+//   0: 8-byte loads, 8 in flight, 16 warps     1: 8-byte loads, 16 in flight, 16 warps
+//   2: 16-byte loads, 8 in flight, 10 warps
+static int mul_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("EFFORT_MUL_VARIANT");
+        v = e ? atoi(e) : 0;
+        if (v < 0 || v > 2) v = 0;
+    }
+    return v;
+}
+
+static constexpr size_t kMaxSmem = 227 * 1024;
+
+template <int SLOTS, int VEC, int U, int NW>
+static int launch_fused(MulProblem pb, int n_cta, int out_dim, int accumulate, float* out,
+                        uint32_t* n_selected_dev, cudaStream_t stream) {
+    pb.g = make_geom<VEC>(pb.C, n_cta);
+    const int per_cta = (pb.in + pb.g.RS - 1) / pb.g.RS;
+    pb.list_cap = ((per_cta * pb.P) + 3) & ~3;
+    const size_t smem = MulSmem<SLOTS, VEC, NW>::bytes(pb.list_cap);
+    if (smem > kMaxSmem) return EFFORT_ESHAPE;
     static size_t configured = 0;
     if (smem > configured) {
-        CK(cudaFuncSetAttribute(bucket_mul_fused_kernel<SLOTS, VEC, U>,
+        CK(cudaFuncSetAttribute(bucket_mul_fused_kernel<SLOTS, VEC, U, NW>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    bucket_mul_fused_kernel<SLOTS, VEC, U><<<grid, kMulThreads, smem, stream>>>(pb);
+    const int grid = pb.g.CS * pb.g.RS;
+    bucket_mul_fused_kernel<SLOTS, VEC, U, NW><<<grid, NW * 32, smem, stream>>>(pb);
     LAUNCHED();
-    (void)ctx;
+    constexpr int TF = SLOTS * 32 * VEC;
+    integrate_kernel<SLOTS, VEC><<<(pb.g.CS * TF + 31) / 32, 256, 0, stream>>>(
+        pb.partial, pb.g, pb.C, accumulate, out, pb.sel_counts, n_selected_dev);
+    LAUNCHED();
+    (void)out_dim;
     return EFFORT_OK;
+}
+
+// floats of partial scratch one problem needs (upper bound over variants)
+static size_t partial_floats(const effort_ctx* ctx, const effort_weights* w) {
+    const int slots = w->kind == EFFORT_KIND_FP16 ? 16 : 32;
+    return (size_t)ctx->n_sms * slots * 32 * 8;
 }
 
 // One fused bucketMul: [fused select+MAC kernel] -> [integrate].  slot = scratch slot inside a batch.
 static int enqueue_bucket_mul(effort_ctx* ctx, const float* v, const effort_weights* w, const uint32_t* exp_no,
                               float* out, double effort, int accumulate, int slot, size_t partial_off,
                               cudaStream_t stream) {
-    const int grid = ctx->n_sms;
     MulProblem pb{};
     pb.v = v; pb.st16 = w->st16; pb.st32 = w->st32; pb.bk = w->fast_bk(); pb.probes = w->probes;
     pb.exp_no = exp_no; pb.cutoff_in = nullptr;
     pb.partial = ctx->partial + partial_off;
-    pb.sel_counts = ctx->sel_counts + (size_t)slot * grid;
+    pb.sel_counts = ctx->sel_counts + (size_t)slot * ctx->n_sms;
     pb.cutoff_out = ctx->cutoff + slot;
     pb.in = w->in; pb.C = w->C; pb.P = w->P; pb.n_probes = w->n_probes;
     pb.q = effort_q(effort, w->n_probes);
     pb.layout = w->layout;
-    const int per_cta = (w->in + grid - 1) / grid;
-    pb.list_cap = ((per_cta * w->P) + 3) & ~3;
-    int rc;
+    pb.trace = ctx->trace;
+    uint32_t* nsel = ctx->sizes + 3 + slot;
     if (w->kind == EFFORT_KIND_FP16) {
-        if (make_geom<4>(w->C).CT * 128 < w->C) return EFFORT_ESHAPE;
-        rc = launch_fused<16, 4, 8>(ctx, pb, grid, stream);
-    } else {
-        if (make_geom<2>(w->C).CT * 64 < w->C) return EFFORT_ESHAPE;
-        rc = launch_fused<32, 2, 8>(ctx, pb, grid, stream);
+        const int variant = (w->C % 8) ? 0 : mul_variant();  // 16-byte loads need C % 8 == 0
+        switch (variant) {
+            case 1: return launch_fused<16, 4, 16, 16>(pb, ctx->n_sms, w->out, accumulate, out, nsel, stream);
+            case 2: return launch_fused<16, 8, 8, 10>(pb, ctx->n_sms, w->out, accumulate, out, nsel, stream);
+            default: return launch_fused<16, 4, 8, 16>(pb, ctx->n_sms, w->out, accumulate, out, nsel, stream);
+        }
     }
-    if (rc) return rc;
-    integrate_kernel<<<(w->out + 255) / 256, 256, 0, stream>>>(pb.partial, grid, w->out, accumulate, out,
-                                                              pb.sel_counts, ctx->sizes + 3 + slot);
-    LAUNCHED();
-    return EFFORT_OK;
+    return launch_fused<32, 2, 8, 16>(pb, ctx->n_sms, w->out, accumulate, out, nsel, stream);
 }
 
-static int ensure_mul_scratch(effort_ctx* ctx, size_t partial_floats, int slots) {
-    int rc = ensure(ctx->partial, ctx->partial_cap, partial_floats);
+static int ensure_mul_scratch(effort_ctx* ctx, size_t partial_floats_needed, int slots) {
+    int rc = ensure(ctx->partial, ctx->partial_cap, partial_floats_needed);
     if (rc) return rc;
     return ensure(ctx->sel_counts, ctx->sel_cap, (size_t)slots * ctx->n_sms);
 }
@@ -282,7 +330,7 @@ extern "C" int effort_bucket_mul(effort_ctx_t* ctx, const float* v_dev, const ef
     if (rc) return rc;
     if (w->kind != EFFORT_KIND_FP16) return EFFORT_EINVAL;  // assert(!goQ8...) bucketMul.swift:72
     if (!w->buckets) return EFFORT_ENOTLOADED;
-    rc = ensure_mul_scratch(ctx, (size_t)ctx->n_sms * w->out, kMaxBatch);
+    rc = ensure_mul_scratch(ctx, partial_floats(ctx, w), kMaxBatch);
     if (rc) return rc;
     return enqueue_bucket_mul(ctx, v_dev, w, exp_no_dev, out_dev, effort, 0, 0, 0, (cudaStream_t)stream_);
 }
@@ -301,7 +349,7 @@ extern "C" int effort_bucket_mul_q4(effort_ctx_t* ctx, const float* v_dev, const
     if (rc) return rc;
     if (w->kind != EFFORT_KIND_Q4) return EFFORT_EINVAL;
     if (!w->buckets) return EFFORT_ENOTLOADED;
-    rc = ensure_mul_scratch(ctx, (size_t)ctx->n_sms * w->out, kMaxBatch);
+    rc = ensure_mul_scratch(ctx, partial_floats(ctx, w), kMaxBatch);
     if (rc) return rc;
     // bucketMulQ4 accumulates into out (atomics, bucketMulQ4.metal:89), then calcOutliers (:61)
     rc = enqueue_bucket_mul(ctx, v_dev, w, exp_no_dev, out_dev, effort, 1, 0, 0, (cudaStream_t)stream_);
@@ -357,7 +405,7 @@ extern "C" int effort_expert_mul_batch(effort_ctx_t* ctx, const effort_mul_args_
     for (int k = 0; k < n; k++) {
         int rc = check_mul_args(ctx, args[k].v_dev, args[k].w, args[k].out_dev, args[k].effort);
         if (rc) return rc;
-        total += (size_t)ctx->n_sms * args[k].w->out;
+        total += partial_floats(ctx, args[k].w);
     }
     int rc = ensure_mul_scratch(ctx, total, kMaxBatch);
     if (rc) return rc;
@@ -365,7 +413,7 @@ extern "C" int effort_expert_mul_batch(effort_ctx_t* ctx, const effort_mul_args_
     for (int k = 0; k < n; k++) {
         rc = expert_mul_one(ctx, args[k], k, off, (cudaStream_t)stream_);
         if (rc) return rc;
-        off += (size_t)ctx->n_sms * args[k].w->out;
+        off += partial_floats(ctx, args[k].w);
     }
     return EFFORT_OK;
 }
@@ -426,18 +474,23 @@ extern "C" int effort_calc_dispatch(effort_ctx_t* ctx, const float* v_dev, const
     return EFFORT_OK;
 }
 
-template <int SLOTS, int VEC, int U>
-static int launch_dispatch_mac(effort_ctx* ctx, const effort_weights* w, int grid, int list_cap,
-                               cudaStream_t stream) {
-    const size_t smem = mul_smem_bytes<SLOTS, VEC>(list_cap);
+template <int SLOTS, int VEC, int U, int NW>
+static int launch_dispatch_mac(effort_ctx* ctx, const effort_weights* w, float* out, cudaStream_t stream) {
+    const MulGeom g = make_geom<VEC>(w->C, ctx->n_sms);
+    const int list_cap = 2048;
+    const size_t smem = MulSmem<SLOTS, VEC, NW>::bytes(list_cap);
     static size_t configured = 0;
     if (smem > configured) {
-        CK(cudaFuncSetAttribute(bucket_mul_dispatch_kernel<SLOTS, VEC, U>,
+        CK(cudaFuncSetAttribute(bucket_mul_dispatch_kernel<SLOTS, VEC, U, NW>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    bucket_mul_dispatch_kernel<SLOTS, VEC, U><<<grid, kMulThreads, smem, stream>>>(
-        w->buckets, ctx->dispatch, ctx->sizes + 1, w->C, list_cap, ctx->partial);
+    bucket_mul_dispatch_kernel<SLOTS, VEC, U, NW><<<g.CS * g.RS, NW * 32, smem, stream>>>(
+        w->buckets, ctx->dispatch, ctx->sizes + 1, w->C, list_cap, g, ctx->partial);
+    LAUNCHED();
+    constexpr int TF = SLOTS * 32 * VEC;
+    integrate_kernel<SLOTS, VEC><<<(g.CS * TF + 31) / 32, 256, 0, stream>>>(
+        ctx->partial, g, w->C, w->kind == EFFORT_KIND_Q4 ? 1 : 0, out, nullptr, nullptr);
     LAUNCHED();
     return EFFORT_OK;
 }
@@ -447,18 +500,10 @@ extern "C" int effort_mul(effort_ctx_t* ctx, const effort_weights_t* w, float* o
     if (!ctx || !w || !out_dev) return EFFORT_EINVAL;
     if (!ctx->have_dispatch || ctx->dispatch_kind != w->kind) return EFFORT_ESTATE;
     if (!w->buckets) return EFFORT_ENOTLOADED;
-    const int grid = ctx->n_sms;
-    int rc = ensure_mul_scratch(ctx, (size_t)grid * w->out, kMaxBatch);
+    int rc = ensure_mul_scratch(ctx, partial_floats(ctx, w), kMaxBatch);
     if (rc) return rc;
-    const int list_cap = 2048;
-    if (w->kind == EFFORT_KIND_FP16) rc = launch_dispatch_mac<16, 4, 8>(ctx, w, grid, list_cap, stream);
-    else rc = launch_dispatch_mac<32, 2, 8>(ctx, w, grid, list_cap, stream);
-    if (rc) return rc;
-    integrate_kernel<<<(w->out + 255) / 256, 256, 0, stream>>>(ctx->partial, grid, w->out,
-                                                              w->kind == EFFORT_KIND_Q4 ? 1 : 0, out_dev,
-                                                              nullptr, nullptr);
-    LAUNCHED();
-    return EFFORT_OK;
+    if (w->kind == EFFORT_KIND_FP16) return launch_dispatch_mac<16, 4, 8, 16>(ctx, w, out_dev, stream);
+    return launch_dispatch_mac<32, 2, 8, 16>(ctx, w, out_dev, stream);
 }
 
 extern "C" int effort_read_dispatch(effort_ctx_t* ctx, float* dispatch_host, size_t capacity,
@@ -517,4 +562,230 @@ extern "C" int effort_bucketize(const void* w_dev, int out_dim, int in_dim, void
 
 extern "C" int effort_q4_bucketize(const void*, int, int, void*, void*, void*, void*) {
     return EFFORT_ESHAPE;  // implemented in a later milestone (q4.cuh)
+}
+
+// ---------------------------------------------------------------------------------------------------
+// decode loop (runNetwork.swift:68-316 mirror)
+// ---------------------------------------------------------------------------------------------------
+#include <map>
+
+#include "decode.cuh"
+
+struct effort_model {
+    effort_ctx* ctx = nullptr;
+    effort_model_config_t cfg{};
+    struct Layer {
+        const effort_weights *wq = nullptr, *wk = nullptr, *wv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr,
+                             *w3 = nullptr;
+        const __half *attn_norm = nullptr, *ffn_norm = nullptr;
+        float *kc = nullptr, *vc = nullptr;
+    };
+    std::vector<Layer> layers;
+    const __half *norm = nullptr, *out_core = nullptr, *emb = nullptr;
+    float *h = nullptr, *h_norm = nullptr, *xq = nullptr, *xk = nullptr, *xv = nullptr, *attn = nullptr,
+          *attn_ffn_out = nullptr, *fxn = nullptr, *x1 = nullptr, *x3 = nullptr, *x2 = nullptr, *ffn_out = nullptr,
+          *out_normed = nullptr, *logits = nullptr;
+    int *pos = nullptr, *token = nullptr, *next = nullptr;
+    int *h_token = nullptr, *h_next = nullptr;  // pinned
+    float* h_logits = nullptr;                  // pinned
+    std::map<int, cudaGraphExec_t> graphs;      // keyed by q = Int(4095*(1-effort))
+    uint64_t launches_per_token = 0;
+    bool use_graphs = true;
+    bool warmed = false;
+    std::vector<void*> owned;
+};
+
+template <typename T>
+static int model_alloc(effort_model* m, T*& p, size_t n) {
+    CK(cudaMalloc(&p, n * sizeof(T)));
+    CK(cudaMemset(p, 0, n * sizeof(T)));
+    m->owned.push_back(p);
+    return EFFORT_OK;
+}
+
+extern "C" int effort_model_create(effort_ctx_t* ctx, const effort_model_config_t* cfg, effort_model_t** m_out) {
+    if (!ctx || !cfg || !m_out) return EFFORT_EINVAL;
+    *m_out = nullptr;
+    if (cfg->head_dim != 128 || cfg->n_heads * cfg->head_dim != cfg->dim) return EFFORT_ESHAPE;
+    if (cfg->n_kv_heads <= 0 || cfg->n_heads % cfg->n_kv_heads) return EFFORT_EINVAL;
+    if (cfg->n_layers <= 0 || cfg->max_seq <= 0 || cfg->vocab <= 0) return EFFORT_EINVAL;
+    if (cfg->tp_size != 1) return EFFORT_ESHAPE;  // sharded decode: see effort_b200/parallel (round 2)
+    effort_model* m = new (std::nothrow) effort_model();
+    if (!m) return EFFORT_ENOMEM;
+    m->ctx = ctx; m->cfg = *cfg;
+    m->layers.resize(cfg->n_layers);
+    const size_t kv = (size_t)cfg->max_seq * cfg->n_kv_heads * cfg->head_dim;
+    int rc = 0;
+    for (auto& l : m->layers) {
+        if ((rc = model_alloc(m, l.kc, kv))) return rc;
+        if ((rc = model_alloc(m, l.vc, kv))) return rc;
+    }
+    const int kvd = cfg->n_kv_heads * cfg->head_dim;
+    if ((rc = model_alloc(m, m->h, cfg->dim)) || (rc = model_alloc(m, m->h_norm, cfg->dim)) ||
+        (rc = model_alloc(m, m->xq, cfg->dim)) || (rc = model_alloc(m, m->xk, kvd)) ||
+        (rc = model_alloc(m, m->xv, kvd)) || (rc = model_alloc(m, m->attn, cfg->dim)) ||
+        (rc = model_alloc(m, m->attn_ffn_out, cfg->dim)) || (rc = model_alloc(m, m->fxn, cfg->dim)) ||
+        (rc = model_alloc(m, m->x1, cfg->hidden_dim)) || (rc = model_alloc(m, m->x3, cfg->hidden_dim)) ||
+        (rc = model_alloc(m, m->x2, cfg->hidden_dim)) || (rc = model_alloc(m, m->ffn_out, cfg->dim)) ||
+        (rc = model_alloc(m, m->out_normed, cfg->dim)) || (rc = model_alloc(m, m->logits, cfg->vocab)) ||
+        (rc = model_alloc(m, m->pos, 1)) || (rc = model_alloc(m, m->token, 1)) || (rc = model_alloc(m, m->next, 1)))
+        return rc;
+    CK(cudaMallocHost(&m->h_token, sizeof(int)));
+    CK(cudaMallocHost(&m->h_next, sizeof(int)));
+    CK(cudaMallocHost(&m->h_logits, sizeof(float) * cfg->vocab));
+    *m_out = m;
+    return EFFORT_OK;
+}
+
+extern "C" int effort_model_destroy(effort_model_t* m) {
+    if (!m) return EFFORT_OK;
+    for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
+    for (void* p : m->owned) cudaFree(p);
+    cudaFreeHost(m->h_token); cudaFreeHost(m->h_next); cudaFreeHost(m->h_logits);
+    delete m;
+    return EFFORT_OK;
+}
+
+extern "C" int effort_model_set_layer(effort_model_t* m, int layer, const effort_weights_t* wq,
+                                      const effort_weights_t* wk, const effort_weights_t* wv,
+                                      const effort_weights_t* wo, const effort_weights_t* w1,
+                                      const effort_weights_t* w2, const effort_weights_t* w3,
+                                      const void* attn_norm_dev, const void* ffn_norm_dev) {
+    if (!m || layer < 0 || layer >= m->cfg.n_layers) return EFFORT_EINVAL;
+    if (!wq || !wk || !wv || !wo || !w1 || !w2 || !w3 || !attn_norm_dev || !ffn_norm_dev) return EFFORT_EINVAL;
+    const auto& c = m->cfg;
+    const int kvd = c.n_kv_heads * c.head_dim;
+    auto ok = [](const effort_weights* w, int in, int out) { return w->in == in && w->out == out; };
+    if (!ok(wq, c.dim, c.dim) || !ok(wk, c.dim, kvd) || !ok(wv, c.dim, kvd) || !ok(wo, c.dim, c.dim) ||
+        !ok(w1, c.dim, c.hidden_dim) || !ok(w3, c.dim, c.hidden_dim) || !ok(w2, c.hidden_dim, c.dim))
+        return EFFORT_ESHAPE;
+    auto& l = m->layers[layer];
+    l.wq = wq; l.wk = wk; l.wv = wv; l.wo = wo; l.w1 = w1; l.w2 = w2; l.w3 = w3;
+    l.attn_norm = (const __half*)attn_norm_dev; l.ffn_norm = (const __half*)ffn_norm_dev;
+    for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
+    m->graphs.clear();
+    return EFFORT_OK;
+}
+
+extern "C" int effort_model_set_head(effort_model_t* m, const void* norm_dev, const void* output_core_dev,
+                                     const void* tok_embeddings_dev) {
+    if (!m || !norm_dev || !output_core_dev || !tok_embeddings_dev) return EFFORT_EINVAL;
+    m->norm = (const __half*)norm_dev; m->out_core = (const __half*)output_core_dev;
+    m->emb = (const __half*)tok_embeddings_dev;
+    return EFFORT_OK;
+}
+
+extern "C" int effort_model_reset(effort_model_t* m, void* stream) {
+    if (!m) return EFFORT_EINVAL;
+    CK(cudaMemsetAsync(m->pos, 0, sizeof(int), (cudaStream_t)stream));
+    return EFFORT_OK;
+}
+
+extern "C" int effort_model_set_graphs(effort_model_t* m, int enable) {
+    if (!m) return EFFORT_EINVAL;
+    m->use_graphs = enable != 0;
+    return EFFORT_OK;
+}
+
+extern "C" const float* effort_model_logits(const effort_model_t* m) { return m ? m->logits : nullptr; }
+extern "C" const int32_t* effort_model_next_token(const effort_model_t* m) { return m ? m->next : nullptr; }
+extern "C" size_t effort_model_bucket_bytes(const effort_model_t* m) {
+    if (!m) return 0;
+    size_t b = 0;
+    for (const auto& l : m->layers)
+        for (const effort_weights* w : {l.wq, l.wk, l.wv, l.wo, l.w1, l.w2, l.w3})
+            if (w) b += (w->kind == EFFORT_KIND_FP16) ? (size_t)w->in * w->out * 2 : (size_t)w->in * w->out / 2;
+    return b;
+}
+
+// enqueue one token (no graph logic).  token lives in m->token (device).
+static int model_enqueue_token(effort_model* m, double effort, cudaStream_t s) {
+    const auto& c = m->cfg;
+    effort_ctx* ctx = m->ctx;
+    if (!m->norm) return EFFORT_ESTATE;
+    embed_kernel<<<4, 1024, 0, s>>>(m->token, m->emb, c.dim, m->h);
+    LAUNCHED();
+    int rc;
+    for (int li = 0; li < c.n_layers; li++) {
+        auto& l = m->layers[li];
+        if (!l.wq) return EFFORT_ESTATE;
+        add_rmsnorm_kernel<<<1, 1024, 0, s>>>(m->h, li ? m->ffn_out : nullptr, l.attn_norm, c.dim, c.norm_eps, m->h_norm);
+        LAUNCHED();
+        effort_mul_args_t qkv[3] = {{m->h_norm, l.wq, nullptr, m->xq, effort},
+                                    {m->h_norm, l.wk, nullptr, m->xk, effort},
+                                    {m->h_norm, l.wv, nullptr, m->xv, effort}};
+        if ((rc = effort_expert_mul_batch(ctx, qkv, 3, s))) return rc;
+        attention_kernel<<<c.n_heads, 256, 0, s>>>(m->xq, m->xk, m->xv, l.kc, l.vc, m->pos, c.n_heads, c.n_kv_heads,
+                                                   c.rope_theta, 0, m->attn);
+        LAUNCHED();
+        effort_mul_args_t wo = {m->attn, l.wo, nullptr, m->attn_ffn_out, effort};
+        if ((rc = effort_expert_mul_batch(ctx, &wo, 1, s))) return rc;
+        add_rmsnorm_kernel<<<1, 1024, 0, s>>>(m->h, m->attn_ffn_out, l.ffn_norm, c.dim, c.norm_eps, m->fxn);
+        LAUNCHED();
+        effort_mul_args_t w13[2] = {{m->fxn, l.w1, nullptr, m->x1, effort}, {m->fxn, l.w3, nullptr, m->x3, effort}};
+        if ((rc = effort_expert_mul_batch(ctx, w13, 2, s))) return rc;
+        silu_mul_kernel<<<(c.hidden_dim + 255) / 256, 256, 0, s>>>(m->x1, m->x3, c.hidden_dim, m->x2);
+        LAUNCHED();
+        effort_mul_args_t w2 = {m->x2, l.w2, nullptr, m->ffn_out, effort};
+        if ((rc = effort_expert_mul_batch(ctx, &w2, 1, s))) return rc;
+    }
+    add_rmsnorm_kernel<<<1, 1024, 0, s>>>(m->h, m->ffn_out, m->norm, c.dim, c.norm_eps, m->out_normed);
+    LAUNCHED();
+    if ((rc = enqueue_basic_mul(m->out_normed, m->out_core, c.vocab, c.dim, m->logits, ctx->n_sms, s))) return rc;
+    argmax_advance_kernel<<<1, 1024, 0, s>>>(m->logits, c.vocab, m->next, m->pos);
+    LAUNCHED();
+    return EFFORT_OK;
+}
+
+extern "C" int effort_model_step(effort_model_t* m, const int32_t* token_dev, double effort, void* stream_) {
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (!m) return EFFORT_EINVAL;
+    if (!(effort >= 0.0 && effort <= 1.0)) return EFFORT_EINVAL;
+    CK(cudaMemcpyAsync(m->token, token_dev ? (const void*)token_dev : (const void*)m->next, sizeof(int),
+                       cudaMemcpyDeviceToDevice, s));
+    const int key = effort_q(effort, EFFORT_PROBES_COUNT);
+    if (!m->use_graphs || s == nullptr) return model_enqueue_token(m, effort, s);  // legacy stream cannot capture
+    auto it = m->graphs.find(key);
+    if (it == m->graphs.end()) {
+        if (!m->warmed) {  // first token: eager (allocates scratch, sets kernel attributes)
+            m->warmed = true;
+            return model_enqueue_token(m, effort, s);
+        }
+        cudaGraph_t g = nullptr;
+        const uint64_t l0 = g_launches.load();
+        CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        int rc = model_enqueue_token(m, effort, s);
+        cudaError_t e = cudaStreamEndCapture(s, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        CK(e);
+        cudaGraphExec_t ge = nullptr;
+        CK(cudaGraphInstantiate(&ge, g, 0));
+        CK(cudaGraphDestroy(g));
+        m->graphs[key] = ge;
+        it = m->graphs.find(key);
+        m->launches_per_token = g_launches.load() - l0;
+        g_launches.store(l0);  // captured, not launched: the replay below counts them
+    }
+    CK(cudaGraphLaunch(it->second, s));
+    g_launches.fetch_add(m->launches_per_token);  // kernels one replay launches
+    return EFFORT_OK;
+}
+
+extern "C" int effort_model_step_host(effort_model_t* m, const int32_t* token_host, double effort,
+                                      int32_t* next_token_host, float* logits_host, void* stream_) {
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (!m) return EFFORT_EINVAL;
+    const int32_t* tok_dev = nullptr;
+    if (token_host) {
+        *m->h_token = *token_host;
+        CK(cudaMemcpyAsync(m->next, m->h_token, sizeof(int), cudaMemcpyHostToDevice, s));  // staged through `next`
+    }
+    int rc = effort_model_step(m, tok_dev, effort, stream_);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(m->h_next, m->next, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (logits_host) CK(cudaMemcpyAsync(m->h_logits, m->logits, sizeof(float) * m->cfg.vocab, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (next_token_host) *next_token_host = *m->h_next;
+    if (logits_host) memcpy(logits_host, m->h_logits, sizeof(float) * m->cfg.vocab);
+    return EFFORT_OK;
 }

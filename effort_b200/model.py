@@ -1,0 +1,155 @@
+"""Host-side mirror of the reference's model containers for the decode loop.
+
+    Model / Layer            loader.swift:201-272   (ExpertWeights per projection, norms, output, embeddings)
+    runNetwork(tokens:effort:)  runNetwork.swift:68  -> DecodeModel.step / step_host (one token per call)
+
+The orchestration itself (layer loop, graph capture) is native code behind the C-ABI (effort_model_* in
+include/effort_b200.h); this module only owns device memory and builds weights.  `random_init` creates a
+random-initialised model of the Mistral-7B architecture (main.swift:45-46,56,72-77) directly on the GPU and
+converts it with the library's own bucketize -- there is no network access for real checkpoints.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib, ops
+from ._lib import ModelConfig, check
+
+
+@dataclass
+class MistralConfig:
+    dim: int = 4096          # stateDim, main.swift:45
+    hidden_dim: int = 14336  # hiddenDim, main.swift:46
+    n_layers: int = 32       # numLayers, main.swift:56
+    n_heads: int = 32        # numHeads, main.swift:72
+    n_kv_heads: int = 8      # kvRepeats = 4, main.swift:73-74
+    head_dim: int = 128
+    vocab: int = 32000
+    max_seq: int = 2048      # maxSeqLen, main.swift:76
+    rope_theta: float = 1e6  # freqs = 1e-6^(j/64), model.swift:701
+    norm_eps: float = 1e-5   # aux.metal:151
+
+
+def _rand_w(out_dim, in_dim, gen, scale=0.02):
+    return (torch.randn((out_dim, in_dim), generator=gen, device="cuda", dtype=torch.float32) * scale).half()
+
+
+class DecodeModel:
+    def __init__(self, cfg: MistralConfig, ctx: Optional[ops.Context] = None):
+        self.cfg = cfg
+        self.ctx = ctx or ops.default_context()
+        self._L = _lib.load()
+        c = ModelConfig(cfg.dim, cfg.hidden_dim, cfg.n_layers, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, cfg.vocab,
+                        cfg.max_seq, cfg.rope_theta, cfg.norm_eps, 0, 1)
+        h = C.c_void_p()
+        check(self._L.effort_model_create(self.ctx._h, C.byref(c), C.byref(h)), "effort_model_create")
+        self._h = h
+        self.layers = []      # keeps ExpertWeights + norm tensors alive
+        self.head = None
+        self._next = C.c_int32(0)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._L.effort_model_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- weights ------------------------------------------------------------------------------------------
+    def set_layer(self, i: int, wq, wk, wv, wo, w1, w2, w3, attn_norm: torch.Tensor, ffn_norm: torch.Tensor):
+        check(self._L.effort_model_set_layer(self._h, i, wq._h, wk._h, wv._h, wo._h, w1._h, w2._h, w3._h,
+                                             attn_norm.data_ptr(), ffn_norm.data_ptr()), "effort_model_set_layer")
+        while len(self.layers) <= i:
+            self.layers.append(None)
+        self.layers[i] = (wq, wk, wv, wo, w1, w2, w3, attn_norm, ffn_norm)
+
+    def set_head(self, norm: torch.Tensor, output_core: torch.Tensor, tok_embeddings: torch.Tensor):
+        check(self._L.effort_model_set_head(self._h, norm.data_ptr(), output_core.data_ptr(),
+                                            tok_embeddings.data_ptr()), "effort_model_set_head")
+        self.head = (norm, output_core, tok_embeddings)
+
+    @classmethod
+    def random_init(cls, cfg: MistralConfig = MistralConfig(), seed: int = 1234, keep_reference_layout: bool = False,
+                    ctx: Optional[ops.Context] = None, norm_jitter: float = 0.1) -> "DecodeModel":
+        """Random-init weights ~ N(0, 0.02^2), converted on the GPU (effort_bucketize)."""
+        m = cls(cfg, ctx)
+        gen = torch.Generator(device="cuda").manual_seed(seed)
+        kvd = cfg.n_kv_heads * cfg.head_dim
+
+        def make(out_dim, in_dim):
+            w = _rand_w(out_dim, in_dim, gen)
+            t = ops.bucketize(w)
+            ew = ops.ExpertWeights(t["buckets"], t["bucket.stats"], t["probes"], inDim=in_dim, outDim=out_dim)
+            if not keep_reference_layout:
+                ew.release_reference_layout()
+            return ew
+
+        def norm_vec():
+            return (1.0 + norm_jitter * torch.randn(cfg.dim, generator=gen, device="cuda")).half()
+
+        for i in range(cfg.n_layers):
+            m.set_layer(i, make(cfg.dim, cfg.dim), make(kvd, cfg.dim), make(kvd, cfg.dim), make(cfg.dim, cfg.dim),
+                        make(cfg.hidden_dim, cfg.dim), make(cfg.dim, cfg.hidden_dim), make(cfg.hidden_dim, cfg.dim),
+                        norm_vec(), norm_vec())
+        m.set_head(norm_vec(), _rand_w(cfg.vocab, cfg.dim, gen), _rand_w(cfg.vocab, cfg.dim, gen, scale=1.0))
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        return m
+
+    # -- run ----------------------------------------------------------------------------------------------
+    def reset(self):
+        check(self._L.effort_model_reset(self._h, ops._stream_ptr()), "effort_model_reset")
+
+    def set_graphs(self, enable: bool):
+        check(self._L.effort_model_set_graphs(self._h, 1 if enable else 0), "effort_model_set_graphs")
+
+    def step(self, token: Optional[torch.Tensor] = None, effort: float = 0.25):
+        """Enqueue one decode step (token: device int32[1]; None = previous prediction)."""
+        check(self._L.effort_model_step(self._h, None if token is None else token.data_ptr(), float(effort),
+                                        ops._stream_ptr()), "effort_model_step")
+
+    def step_host(self, token: Optional[int] = None, effort: float = 0.25, logits=None) -> int:
+        """End-to-end step with host buffers: H2D token, decode, D2H next token (+ logits into a numpy array)."""
+        tok = None
+        if token is not None:
+            tok = C.c_int32(int(token))
+        nxt = C.c_int32(0)
+        check(self._L.effort_model_step_host(self._h, None if tok is None else C.byref(tok), float(effort),
+                                             C.byref(nxt), None if logits is None else logits.ctypes.data,
+                                             ops._stream_ptr()), "effort_model_step_host")
+        return int(nxt.value)
+
+    def logits(self) -> torch.Tensor:
+        """Device logits of the last step as a torch view (copy)."""
+        import numpy as np
+        n = self.cfg.vocab
+        out = torch.empty(n, dtype=torch.float32, device="cuda")
+        ptr = self._L.effort_model_logits(self._h)
+        from ctypes import c_void_p
+        # device-to-device copy through torch: wrap the raw pointer
+        src = _tensor_from_ptr(ptr, n)
+        out.copy_(src)
+        return out
+
+    def next_token(self) -> int:
+        ptr = self._L.effort_model_next_token(self._h)
+        return int(_tensor_from_ptr(ptr, 1, torch.int32).cpu()[0])
+
+    @property
+    def bucket_bytes(self) -> int:
+        return int(self._L.effort_model_bucket_bytes(self._h))
+
+
+class _CudaArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def _tensor_from_ptr(ptr, n, dtype=torch.float32) -> torch.Tensor:
+    typestr = "<f4" if dtype == torch.float32 else "<i4"
+    return torch.as_tensor(_CudaArray(ptr, n, typestr), device="cuda")

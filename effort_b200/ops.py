@@ -108,6 +108,12 @@ class ExpertWeights:
               "effort_weights_create")
         self._h, self._L = h, L
 
+    def release_reference_layout(self):
+        """Drop the caller-layout tensors (the handle owns a repacked copy + probes).  Afterwards only the fast
+        path may be used: the calcDispatch/mul test hooks read the reference layout."""
+        if self.buckets is not None and self.owned_bytes > 0:
+            self.buckets = self.stats = self.probes = None
+
     @property
     def expertSize(self) -> int:  # loader.swift:50
         return self.percentLoad * self.inSize

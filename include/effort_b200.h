@@ -152,6 +152,60 @@ int effort_bucketize(const void* w_dev, int out_dim, int in_dim, void* buckets_d
 int effort_q4_bucketize(const void* wT_dev, int in_dim, int out_dim, void* buckets_dev, void* stats_dev,
                         void* probes_dev, void* stream);
 
+/* ---- decode loop (host orchestration of the callers either side of the path) ----------------------- */
+/*
+ * runNetwork(tokens:effort:)  runNetwork.swift:68-316, one token per call: per layer rmsNormFast*attnNorm,
+ * expertMul x3 (wq,wk,wv), rope_mx + calcScores + softmax + sumScores, expertMul wo, residual, rmsNormFast*
+ * ffnNorm, expertMul w1,w3, silu, expertMul w2, residual (:124-183); final rmsNorm*norm and the dense
+ * lm_head basicMul (:206-209); greedy next token = top-1 (:235-257).  north_star keeps this orchestration in
+ * Swift; there is no Swift toolchain here, so the mirror lives behind the same C-ABI and a Swift build would
+ * call the per-operator entry points above instead.  Dims follow main.swift:45-46,56,72-77.
+ */
+typedef struct effort_model effort_model_t;
+typedef struct {
+    int dim;         /* stateDim 4096 */
+    int hidden_dim;  /* hiddenDim 14336 */
+    int n_layers;    /* numLayers 32 */
+    int n_heads;     /* numHeads 32 */
+    int n_kv_heads;  /* 8 (kvRepeats = 4) */
+    int head_dim;    /* headDim 128 (the attention kernel requires 128) */
+    int vocab;       /* 32000 */
+    int max_seq;     /* maxSeqLen 2048 */
+    float rope_theta;/* 1e6: freqs = 1e-6^(j/64), model.swift:701 */
+    float norm_eps;  /* 1e-5, aux.metal:151 */
+    int tp_rank, tp_size; /* tensor-parallel shard of this process (1 = unsharded); see DESIGN.md section 6 */
+} effort_model_config_t;
+
+int effort_model_create(effort_ctx_t* ctx, const effort_model_config_t* cfg, effort_model_t** m_out);
+int effort_model_destroy(effort_model_t* m);
+/* Layer weights (loader.swift:201-225).  The handles and norm vectors (fp16 [dim]) stay owned by the caller. */
+int effort_model_set_layer(effort_model_t* m, int layer, const effort_weights_t* wq, const effort_weights_t* wk,
+                           const effort_weights_t* wv, const effort_weights_t* wo, const effort_weights_t* w1,
+                           const effort_weights_t* w2, const effort_weights_t* w3, const void* attn_norm_dev,
+                           const void* ffn_norm_dev);
+/* model.norm [dim] f16, output.core [vocab,dim] f16, tok_embeddings.core [vocab,dim] f16 (loader.swift:254-272) */
+int effort_model_set_head(effort_model_t* m, const void* norm_dev, const void* output_core_dev,
+                          const void* tok_embeddings_dev);
+/* position <- 0 (the KV cache is logically emptied) */
+int effort_model_reset(effort_model_t* m, void* stream);
+/*
+ * One decode step at the current position, enqueue-only.  token_dev: device int32 (NULL = the token the
+ * previous step predicted).  After it: logits in effort_model_logits(), next token in effort_model_next_token().
+ * The first call for a given effort value runs eagerly and captures a CUDA graph; later calls replay it.
+ */
+int effort_model_step(effort_model_t* m, const int32_t* token_dev, double effort, void* stream);
+/* Same step driven with HOST buffers (the end-to-end call): token_host (NULL = previous prediction) is copied
+ * H2D from pinned memory, the step runs, next token (and logits if logits_host != NULL) are copied D2H and the
+ * stream is synchronised. */
+int effort_model_step_host(effort_model_t* m, const int32_t* token_host, double effort, int32_t* next_token_host,
+                           float* logits_host, void* stream);
+const float* effort_model_logits(const effort_model_t* m);        /* device [vocab] f32 */
+const int32_t* effort_model_next_token(const effort_model_t* m);  /* device int32 */
+/* bytes of bucket weights one token streams at effort 1.0 (sum of in*out*2 over the 7x n_layers matrices) */
+size_t effort_model_bucket_bytes(const effort_model_t* m);
+/* use CUDA graphs for effort_model_step (default 1) */
+int effort_model_set_graphs(effort_model_t* m, int enable);
+
 /* ---- introspection used by bench / tests -------------------------------- */
 /* number of kernels this library has launched since load (process-wide) */
 uint64_t effort_launch_count(void);

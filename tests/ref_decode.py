@@ -1,0 +1,69 @@
+"""CPU restatement of one decode step (runNetwork.swift:113-209) on top of the oracle's bucketMul.
+Test infrastructure only.  Glue ops follow aux.metal / matrix.metal (cited inline)."""
+import numpy as np
+
+from oracle import oracle as O
+
+
+def rmsnorm_mul(x, w, eps=1e-5):
+    """rmsNorm32fast (aux.metal:113-152) then mulVec32by16 (aux.metal:269)."""
+    x = x.astype(np.float32)
+    ss = np.float32(np.sum(x.astype(np.float64) ** 2))
+    denom = np.sqrt(np.float32(ss / np.float32(x.size) + np.float32(eps)))
+    return ((x / denom) * w.astype(np.float32)).astype(np.float32)
+
+
+def rope(x, pos, theta=1e6, hd=128):
+    """rope_mx (aux.metal:218-231) with freqs = (1/theta)^(j/64) (model.swift:693-717)."""
+    x = x.reshape(-1, hd).astype(np.float32)
+    j = np.arange(hd // 2)
+    freq = np.power(np.float32(1.0 / theta), (j / np.float32(hd // 2)).astype(np.float32)).astype(np.float32)
+    ang = (np.float32(pos) * freq).astype(np.float32)
+    c, s = np.cos(ang), np.sin(ang)
+    out = np.empty_like(x)
+    out[:, : hd // 2] = x[:, : hd // 2] * c - x[:, hd // 2:] * s
+    out[:, hd // 2:] = x[:, hd // 2:] * c + x[:, : hd // 2] * s
+    return out.reshape(-1)
+
+
+class RefModel:
+    """weights: list of layers, each dict name -> dict(buckets, stats, probes, in, out) + 'attn_norm','ffn_norm'."""
+
+    def __init__(self, layers, norm, out_core, emb, n_heads=32, n_kv=8, hd=128):
+        self.layers, self.norm, self.out_core, self.emb = layers, norm, out_core, emb
+        self.n_heads, self.n_kv, self.hd = n_heads, n_kv, hd
+        self.kc = [[] for _ in layers]
+        self.vc = [[] for _ in layers]
+        self.pos = 0
+
+    def _mul(self, v, w, effort):
+        r = O.bucket_mul(v, w["buckets"], w["stats"], w["probes"], w["in"], w["out"], effort)
+        return r["out32"]
+
+    def step(self, token, effort):
+        h = self.emb[token].astype(np.float32)
+        for li, L in enumerate(self.layers):
+            hn = rmsnorm_mul(h, L["attn_norm"])
+            xq, xk, xv = self._mul(hn, L["wq"], effort), self._mul(hn, L["wk"], effort), self._mul(hn, L["wv"], effort)
+            q = rope(xq, self.pos).reshape(self.n_heads, self.hd)
+            k = rope(xk, self.pos).reshape(self.n_kv, self.hd)
+            self.kc[li].append(k)
+            self.vc[li].append(xv.reshape(self.n_kv, self.hd).copy())
+            K = np.stack(self.kc[li])  # [T, n_kv, hd]
+            V = np.stack(self.vc[li])
+            out = np.empty((self.n_heads, self.hd), np.float32)
+            rep = self.n_heads // self.n_kv
+            for hh in range(self.n_heads):
+                sc = (K[:, hh // rep, :] @ q[hh]) / np.float32(np.sqrt(self.hd))   # dotSetScore2 aux.metal:445
+                p = np.exp(sc.astype(np.float32))                                  # softmax without max (aux.metal:185-199)
+                p = p / p.sum()
+                out[hh] = p @ V[:, hh // rep, :]                                   # sumScores32 aux.metal:379-393
+            h = h + self._mul(out.reshape(-1), L["wo"], effort)
+            fx = rmsnorm_mul(h, L["ffn_norm"])
+            x1, x3 = self._mul(fx, L["w1"], effort), self._mul(fx, L["w3"], effort)
+            x2 = (x3 * x1 / (1.0 + np.exp(-x1))).astype(np.float32)               # silu32b matrix.metal:25-34
+            h = h + self._mul(x2, L["w2"], effort)
+        on = rmsnorm_mul(h, self.norm)
+        logits, _ = O.basic_mul(on, self.out_core, cast_v=True)                    # runNetwork.swift:209
+        self.pos += 1
+        return logits
