@@ -70,7 +70,7 @@ struct MulProblem {
     int in, C, P, n_probes, q, layout;
     int list_cap;             // capacity of the shared-memory row list (entries)
     MulGeom g;
-    unsigned long long* trace;  // optional [grid][8] phase timestamps (globaltimer ns), debugging aid
+    unsigned long long* trace;  // optional [grid][16] phase timestamps (globaltimer ns), debugging aid
 };
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -80,7 +80,7 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
 }
 #define EFFORT_TRACE(k)                                                                    \
     do {                                                                                   \
-        if (pb.trace && threadIdx.x == 0) pb.trace[(size_t)blockIdx.x * 8 + (k)] = gtime_ns(); \
+        if (pb.trace && threadIdx.x == 0) pb.trace[(size_t)blockIdx.x * 16 + (k)] = gtime_ns(); \
     } while (0)
 
 // ---- shared-memory accumulate ---------------------------------------------------------------------
@@ -99,6 +99,16 @@ template <int IMM>
 __device__ __forceinline__ void sts_imm(uint32_t addr, float x) {
     asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(addr), "n"(IMM), "f"(x));
 }
+
+constexpr int kMulBatchMax = 4;
+constexpr int EFFORT_PROBES_MAX = 4096;  // probesCount (bucketMul.swift:19): the fused path supports exactly this
+// Several independent problems in ONE launch (q/k/v share v, runNetwork.swift:132-134; w1/w3, :178-179):
+// CTAs [cta_begin[p], cta_begin[p+1]) work on problem p.
+struct MulBatch {
+    int n;
+    int cta_begin[kMulBatchMax + 1];
+    MulProblem p[kMulBatchMax];
+};
 
 template <int VEC>
 struct TileBits {
@@ -177,22 +187,23 @@ __device__ __forceinline__ void accumulate_words(uint32_t base_lane, float val,
 }
 
 template <int VEC>
-__device__ __forceinline__ void load_words(const uint16_t* p, uint32_t (&words)[(VEC + 1) / 2]) {
+__device__ __forceinline__ void load_words(const uint16_t* p, uint32_t (&words)[(VEC + 1) / 2], uint64_t pol) {
     if constexpr (VEC == 8) {
-        uint4 d = ldg_stream_u4(p);
+        uint4 d = ldg_stream_u4(p, pol);
         words[0] = d.x; words[1] = d.y; words[2] = d.z; words[3] = d.w;
     } else if constexpr (VEC == 4) {
-        uint2 d = ldg_stream_u2(p);
+        uint2 d = ldg_stream_u2(p, pol);
         words[0] = d.x; words[1] = d.y;
     } else {
-        words[0] = ldg_stream_u1(p);
+        words[0] = ldg_stream_u1(p, pol);
     }
 }
 
 // ---- streaming: one warp walks its share of the row list --------------------------------------------
 // list entries are {float val, uint32 rowOffset} read with one 8-byte broadcast LDS.  The loop is branch
-// free: an entry past the end (or a lane past the last column) loads nothing and adds 0.0 into the
-// lane's own words.
+// free (an entry past the end, or a lane past the last column, loads nothing and adds 0.0 into the lane's
+// own words) and SOFTWARE PIPELINED: the U loads of batch n+1 are in flight while batch n is accumulated, so
+// every lane always has U..2U vector loads outstanding (HBM latency x bandwidth needs ~40 KB per SM).
 template <int SLOTS, int VEC, int U, int NW>
 __device__ __forceinline__ void stream_rows(const uint2* __restrict__ list, int n_list,
                                             const uint16_t* __restrict__ bk, int C, int slice,
@@ -206,24 +217,35 @@ __device__ __forceinline__ void stream_rows(const uint2* __restrict__ list, int 
     const int stride = NW * g.R;  // list entries consumed per step by all warps
     const int first = warp * g.R + rowslot;
     const int nsteps = (n_list + stride - 1) / stride;
-    for (int n0 = 0; n0 < nsteps; n0 += U) {
-        uint32_t words[U][(VEC + 1) / 2];
-        float val[U];
+    const uint64_t pol = l2_policy_evict_first();
+    constexpr int NWD = (VEC + 1) / 2;
+    uint32_t wa[U][NWD], wb[U][NWD];
+    float va[U], vb[U];
+    auto load_batch = [&](int n0, uint32_t (&w)[U][NWD], float (&val)[U]) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int e = (n0 + u) * stride + first;
             const bool ok = lane_on && (e < n_list);
             val[u] = 0.f;
 #pragma unroll
-            for (int j = 0; j < (VEC + 1) / 2; j++) words[u][j] = 0u;
+            for (int j = 0; j < NWD; j++) w[u][j] = 0u;
             if (ok) {
                 const uint2 ent = list[e];
                 val[u] = __uint_as_float(ent.x);
-                load_words<VEC>(bk_col + (size_t)ent.y, words[u]);
+                load_words<VEC>(bk_col + (size_t)ent.y, w[u], pol);
             }
         }
+    };
+    auto process_batch = [&](const uint32_t (&w)[U][NWD], const float (&val)[U]) {
 #pragma unroll
-        for (int u = 0; u < U; u++) accumulate_words<SLOTS, VEC>(base_lane, val[u], words[u]);
+        for (int u = 0; u < U; u++) accumulate_words<SLOTS, VEC>(base_lane, val[u], w[u]);
+    };
+    load_batch(0, wa, va);
+    for (int n0 = 0; n0 < nsteps; n0 += 2 * U) {
+        load_batch(n0 + U, wb, vb);
+        process_batch(wa, va);
+        load_batch(n0 + 2 * U, wa, va);
+        process_batch(wb, vb);
     }
 }
 
@@ -283,12 +305,21 @@ __device__ __forceinline__ void reduce_tiles_to_partial(const float* __restrict_
                                                         float* __restrict__ partial) {
     constexpr int TF = MulSmem<SLOTS, VEC, NW>::kTileFloats;
     for (int idx = threadIdx.x; idx < TF; idx += NW * 32) {
-        const int lane = idx & 31;
-        float sum = 0.f;
-        if (lane < g.lpr) {
-            for (int rs = 0; rs < g.R; rs++)
+        float a[NW];
 #pragma unroll
-                for (int w = 0; w < NW; w++) sum += tiles[(size_t)w * TF + idx + rs * g.lpr];
+        for (int w = 0; w < NW; w++) a[w] = tiles[(size_t)w * TF + idx];  // NW independent conflict-free loads
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; w++) sum += a[w];
+        if (g.R > 1) {  // sub-warp rows: fold the row slots into lanes < lpr
+            const int lane = idx & 31;
+            if (lane < g.lpr) {
+                for (int rs = 1; rs < g.R; rs++)
+#pragma unroll
+                    for (int w = 0; w < NW; w++) sum += tiles[(size_t)w * TF + idx + rs * g.lpr];
+            } else {
+                sum = 0.f;
+            }
         }
         partial[idx] = sum;
     }
@@ -297,7 +328,7 @@ __device__ __forceinline__ void reduce_tiles_to_partial(const float* __restrict_
 // ---- fused kernel: cutoff (optional) + selection + gather-MAC + CTA partial -------------------------
 template <int SLOTS, int VEC, int U, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
-bucket_mul_fused_kernel(const MulProblem pb) {
+bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using L = MulSmem<SLOTS, VEC, NW>;
     constexpr int NT = NW * 32;
@@ -305,20 +336,28 @@ bucket_mul_fused_kernel(const MulProblem pb) {
     MulSmemHeader<NW>& hdr = *sv.hdr;
     uint2* list = sv.list;
 
+    int pi = 0;
+#pragma unroll
+    for (int k = 1; k < kMulBatchMax; k++) pi += (k < batch.n && (int)blockIdx.x >= batch.cta_begin[k]) ? 1 : 0;
+    const MulProblem& pb = batch.p[pi];
+    const int lb = (int)blockIdx.x - batch.cta_begin[pi];  // CTA index inside the problem
+
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t e_no = pb.exp_no ? *pb.exp_no : 0u;
     const MulGeom g = pb.g;
-    const int slice = (int)blockIdx.x % g.CS, rsp = (int)blockIdx.x / g.CS;
+    const int slice = lb % g.CS, rsp = lb / g.CS;
 
     EFFORT_TRACE(0);
     zero_my_tile<SLOTS, VEC, NW>(sv.tiles);  // independent of everything else: overlaps the loads below
+    EFFORT_TRACE(1);
 
     // 0. issue every global load the selection needs BEFORE the cutoff is known (they do not depend on
     //    it): thread <-> input dim i = rsp + j*RS, its v[i] and its P stats (32 contiguous bytes in the
     //    input-major repack).  One DRAM/L2 round trip for the whole prologue instead of one per stage.
     const int P = pb.P;
+    const uint64_t keep = l2_policy_evict_last();
     const int n_in = (pb.in > rsp) ? (pb.in - 1 - rsp) / g.RS + 1 : 0;
-    constexpr int KSEL = 2;  // inputs per thread held in registers; more are handled by the tail loop
+    constexpr int KSEL = 1;  // inputs per thread held in registers; more are handled by the tail loop
     float sel_v[KSEL];
     float sel_stat[KSEL][16];
 #pragma unroll
@@ -333,7 +372,7 @@ bucket_mul_fused_kernel(const MulProblem pb) {
             if constexpr (SLOTS == 16) {
                 if (pb.layout == kInputMajor && P == 16) {
                     const uint4* sp = reinterpret_cast<const uint4*>(pb.st16 + ((size_t)e_no * pb.in + i) * 16);
-                    const uint4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+                    const uint4 s0 = ldg_keep_u4(sp, keep), s1 = ldg_keep_u4(sp + 1, keep);
                     const uint32_t ws[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
                     for (int q2 = 0; q2 < 8; q2++) {
@@ -359,19 +398,21 @@ bucket_mul_fused_kernel(const MulProblem pb) {
         }
     }
 
+    EFFORT_TRACE(2);
     // 1. cutoff (every CTA redundantly: 24 KB of L2-resident inputs, no extra launch / global round trip)
     float cutoff;
     if (pb.cutoff_in) {
         cutoff = *pb.cutoff_in;
     } else {
-        constexpr int PER = (kCutoffThreads * kCutoffMaxPerThread + NT - 1) / NT;
+        constexpr int PER = (EFFORT_PROBES_MAX + NT - 1) / NT;
         float vals[PER];
-        score_probes(pb.v, pb.probes, e_no, pb.n_probes, vals);
-        EFFORT_TRACE(1);
-        cutoff = block_bisect_cutoff(vals, pb.n_probes, pb.q, hdr.cut, nullptr);
+        score_probes(pb.v, pb.probes, e_no, pb.n_probes, vals, keep);
+        EFFORT_TRACE(3);
+        cutoff = block_bisect_cutoff(vals, pb.n_probes, pb.q, hdr.cut, nullptr,
+                                     pb.trace ? pb.trace + (size_t)blockIdx.x * 16 : nullptr);
     }
-    if (pb.cutoff_out && blockIdx.x == 0 && tid == 0) *pb.cutoff_out = cutoff;
-    EFFORT_TRACE(2);
+    if (pb.cutoff_out && lb == 0 && tid == 0) *pb.cutoff_out = cutoff;
+    EFFORT_TRACE(6);
 
     // 2. selection + compaction.  Thread order == (input, rank) order == ascending row order, so the list
     //    is deterministic and consecutive entries are consecutive rows in HBM.
@@ -402,6 +443,7 @@ bucket_mul_fused_kernel(const MulProblem pb) {
             }
             cnt += __popc(mask[k]);
         }
+        EFFORT_TRACE(7);
         // block exclusive scan of cnt (order: k-major inside a thread is NOT input order, so scan per k)
 #pragma unroll
         for (int k = 0; k < KSEL; k++) {
@@ -455,17 +497,17 @@ bucket_mul_fused_kernel(const MulProblem pb) {
     const int n_list = base;
     if (pb.sel_counts && slice == 0 && tid == 0) pb.sel_counts[rsp] = (uint32_t)n_list;
     __syncthreads();  // list + zeroed tiles visible
-    EFFORT_TRACE(3);
+    EFFORT_TRACE(8);
 
     // 3. stream the selected rows
     stream_rows<SLOTS, VEC, U, NW>(list, n_list, pb.bk, pb.C, slice, g,
                                    sv.tiles_saddr + (uint32_t)warp * L::kTileBytes);
     __syncthreads();
-    EFFORT_TRACE(4);
+    EFFORT_TRACE(9);
 
     // 4. CTA partial (tile layout)
-    reduce_tiles_to_partial<SLOTS, VEC, NW>(sv.tiles, g, pb.partial + (size_t)blockIdx.x * L::kTileFloats);
-    EFFORT_TRACE(5);
+    reduce_tiles_to_partial<SLOTS, VEC, NW>(sv.tiles, g, pb.partial + (size_t)lb * L::kTileFloats);
+    EFFORT_TRACE(10);
 }
 
 // ---- test-hook kernel: MAC over a reference-format dispatch list (BucketMul.mul) --------------------
@@ -507,20 +549,34 @@ bucket_mul_dispatch_kernel(const uint16_t* __restrict__ bk, const float2* __rest
 // Block = 8 warps x 32 consecutive tile words: warp w sums the partials r = w (mod 8) (coalesced 128-byte
 // rows, all loads independent), shared-memory fold, then warp 0 un-permutes tile word -> output index.
 // accumulate != 0 keeps the Q4 semantics (adds INTO out, bucketMulQ4.metal:89).
+struct IntegrateItem {
+    const float* partial;
+    float* out;
+    const uint32_t* sel_counts;
+    uint32_t* n_selected;
+    MulGeom g;
+    int C, accumulate;
+};
+struct IntegrateBatch {
+    int n;
+    IntegrateItem it[kMulBatchMax];
+};
+
 template <int SLOTS, int VEC>
 __global__ void __launch_bounds__(256)
-integrate_kernel(const float* __restrict__ partial, const MulGeom g, int C, int accumulate,
-                 float* __restrict__ out_vec, const uint32_t* __restrict__ sel_counts,
-                 uint32_t* __restrict__ n_selected) {
+integrate_kernel(const __grid_constant__ IntegrateBatch ib) {
     constexpr int TW = 32 * VEC;
     constexpr int TF = SLOTS * TW;
     __shared__ float red[8][32];
+    const IntegrateItem& it = ib.it[blockIdx.y];
+    const MulGeom g = it.g;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + lane;  // word index in [0, CS*TF)
+    if (blockIdx.x * 32 >= g.CS * TF) return;  // whole block past this problem's words (block uniform)
     const int slice = j / TF, idx = j % TF;
     float s = 0.f;
     if (slice < g.CS) {
-        const float* p = partial + (size_t)slice * TF + idx;
+        const float* p = it.partial + (size_t)slice * TF + idx;
         const size_t rstride = (size_t)g.CS * TF;
 #pragma unroll 4
         for (int r = w; r < g.RS; r += 8) s += p[(size_t)r * rstride];
@@ -534,16 +590,16 @@ integrate_kernel(const float* __restrict__ partial, const MulGeom g, int C, int 
         const int slot = idx / TW, k = (idx % TW) / 32;
         if (lane < g.lpr) {
             const int col = slice * TW + lane * VEC + k;
-            if (col < C) {
+            if (col < it.C) {
                 const int o = col * SLOTS + slot;
-                out_vec[o] = accumulate ? out_vec[o] + t : t;
+                it.out[o] = it.accumulate ? it.out[o] + t : t;
             }
         }
     }
-    if (n_selected && sel_counts && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (it.n_selected && it.sel_counts && blockIdx.x == 0 && threadIdx.x == 0) {
         uint32_t t = 0;
-        for (int r = 0; r < g.RS; r++) t += sel_counts[r];
-        *n_selected = t;
+        for (int r = 0; r < g.RS; r++) t += it.sel_counts[r];
+        *it.n_selected = t;
     }
 }
 

@@ -49,6 +49,48 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
     return r;
 }
 
+// L2 eviction policies: bucket rows are read once per token (evict_first) while the small per-matrix
+// metadata (stats, probes: ~41 MB for Mistral-7B) and the activations should stay L2 resident across the
+// 14 GB that stream through between two uses (evict_last).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint2 ldg_stream_u2(const void* p, uint64_t pol) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
+                 : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_stream_u4(const void* p, uint64_t pol) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u1(const void* p, uint64_t pol) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_keep_u4(const void* p, uint64_t pol) {
+    uint4 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint16_t ldg_keep_u16(const void* p, uint64_t pol) {
+    uint16_t r;
+    asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(r) : "l"(p), "l"(pol));
+    return r;
+}
+
 __device__ __forceinline__ int warp_sum_i(int x) { return __reduce_add_sync(0xffffffffu, x); }
 __device__ __forceinline__ float warp_sum_f(float x) {
 #pragma unroll

@@ -26,10 +26,10 @@ constexpr int kCutoffThreads = 1024;
 constexpr int kCutoffMaxPerThread = 8;  // n_probes <= 8192 for the stand-alone kernel
 constexpr int kCutoffInsideMax = 128;   // phase-B capacity (4 per lane)
 
-struct CutoffSmem {
+struct __align__(16) CutoffSmem {
+    int cnt[2][32];
     float red_min[32];
     float red_max[32];
-    int cnt[2][32];
     float inside[kCutoffInsideMax];
     int n_inside;
     float result;
@@ -63,7 +63,8 @@ __device__ __forceinline__ bool bisect_step(BisectState& s, int countAbove, int 
 // thread.  `loops_out` (may be null) receives the reference's iteration count from thread 0.
 template <int PER>
 __device__ __forceinline__ float block_bisect_cutoff(const float (&vals)[PER], int n_probes, int q,
-                                                     CutoffSmem& sm, int* loops_out) {
+                                                     CutoffSmem& sm, int* loops_out,
+                                                     unsigned long long* trace = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     float tmin = 999.f, tmax = -999.f;  // bucketMul.metal:155-156
 #pragma unroll
@@ -76,6 +77,7 @@ __device__ __forceinline__ float block_bisect_cutoff(const float (&vals)[PER], i
     }
     if (lane == 0) { sm.red_min[warp] = tmin; sm.red_max[warp] = tmax; }
     if (tid == 0) sm.n_inside = 0;
+    if (tid < 64) (&sm.cnt[0][0])[tid] = 0;  // slots of absent warps must read as 0
     __syncthreads();
     float gmin = (lane < nwarps) ? sm.red_min[lane] : 999.f;
     float gmax = (lane < nwarps) ? sm.red_max[lane] : -999.f;
@@ -93,6 +95,7 @@ __device__ __forceinline__ float block_bisect_cutoff(const float (&vals)[PER], i
     const int effort = n_probes - q;                 // :154
     bool done = false, fixpoint = false;
     int buf = 0;
+    if (trace && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[4] = t; }
     // ---- phase A: block-wide rounds (state replicated in every thread, identical by construction) ----
     while (!done && (s.minCount - s.maxCount) > kCutoffInsideMax) {
         s.loops++;
@@ -102,10 +105,16 @@ __device__ __forceinline__ float block_bisect_cutoff(const float (&vals)[PER], i
         c = warp_sum_i(c);
         if (lane == 0) sm.cnt[buf][warp] = c;
         __syncthreads();
-        const int countAbove = warp_sum_i((lane < nwarps) ? sm.cnt[buf][lane] : 0);
+        int countAbove = 0;
+#pragma unroll
+        for (int w4 = 0; w4 < 8; w4++) {  // 32 warp counts, broadcast 16-byte reads (unused slots are 0)
+            const int4 q4 = *reinterpret_cast<const int4*>(&sm.cnt[buf][w4 * 4]);
+            countAbove += q4.x + q4.y + q4.z + q4.w;
+        }
         buf ^= 1;
         done = bisect_step(s, countAbove, effort, fixpoint);
     }
+    if (trace && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[5] = t; trace[11] = (unsigned long long)s.loops; }
     if (!done) {
         // ---- compact the products inside (minBound, maxBound] ----
 #pragma unroll
@@ -129,10 +138,11 @@ __device__ __forceinline__ float block_bisect_cutoff(const float (&vals)[PER], i
             const int above_max = s.maxCount;
             while (!done) {
                 s.loops++;
-                int c = 0;
+                int c = above_max;
 #pragma unroll
-                for (int k = 0; k < kCutoffInsideMax / 32; k++) c += (x[k] > s.newBound) ? 1 : 0;
-                const int countAbove = above_max + warp_sum_i(c);
+                for (int k = 0; k < kCutoffInsideMax / 32; k++)
+                    c += __popc(__ballot_sync(0xffffffffu, x[k] > s.newBound));
+                const int countAbove = c;
                 done = bisect_step(s, countAbove, effort, fixpoint);
             }
             if (lane == 0) { sm.result = s.newBound; sm.loops = s.loops; }
@@ -142,18 +152,21 @@ __device__ __forceinline__ float block_bisect_cutoff(const float (&vals)[PER], i
         s.loops = sm.loops;
     }
     if (loops_out && tid == 0) *loops_out = s.loops;
+    if (trace && tid == 0) trace[12] = (unsigned long long)s.loops;
     return s.newBound;
 }
 
 // Scores this thread's probes: thread t owns probes t, t+NT, ...  (bucketMul.metal:158-163)
 template <int PER>
 __device__ __forceinline__ void score_probes(const float* __restrict__ v, const __half* __restrict__ probes,
-                                             uint32_t exp_no, int n_probes, float (&vals)[PER]) {
+                                             uint32_t exp_no, int n_probes, float (&vals)[PER],
+                                             uint64_t keep) {
 #pragma unroll
     for (int k = 0; k < PER; k++) {
         int i = threadIdx.x + k * blockDim.x;
         if (i < n_probes) {
-            float p = bf16_round(__half2float(probes[(size_t)exp_no * n_probes + i]));
+            const uint16_t pb16 = ldg_keep_u16(probes + (size_t)exp_no * n_probes + i, keep);
+            float p = bf16_round(__half2float(__ushort_as_half(pb16)));
             float x = __fmul_rn(__fmul_rn(kCutoffScale, v[i]), p);
             vals[k] = bf16_round(fabsf(x));
         } else {
@@ -170,7 +183,7 @@ find_cutoff_kernel(const float* __restrict__ v, const __half* __restrict__ probe
     __shared__ CutoffSmem sm;
     const uint32_t exp_no = exp_no_dev ? *exp_no_dev : 0u;
     float vals[kCutoffMaxPerThread];
-    score_probes<kCutoffMaxPerThread>(v, probes, exp_no, n_probes, vals);
+    score_probes<kCutoffMaxPerThread>(v, probes, exp_no, n_probes, vals, l2_policy_evict_last());
     float c = block_bisect_cutoff<kCutoffMaxPerThread>(vals, n_probes, q, sm, loops_out);
     if (threadIdx.x == 0) *cutoff_out = c;
 }

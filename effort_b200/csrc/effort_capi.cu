@@ -117,8 +117,8 @@ extern "C" int effort_ctx_create(int device, effort_ctx_t** ctx_out) {
     CK(cudaMemset(c->cutoff, 0, sizeof(float) * kMaxBatch));
     CK(cudaMemset(c->loops, 0, sizeof(int)));
     if (getenv("EFFORT_TRACE")) {
-        CK(cudaMalloc(&c->trace, sizeof(unsigned long long) * 8 * c->n_sms));
-        CK(cudaMemset(c->trace, 0, sizeof(unsigned long long) * 8 * c->n_sms));
+        CK(cudaMalloc(&c->trace, sizeof(unsigned long long) * 16 * c->n_sms));
+        CK(cudaMemset(c->trace, 0, sizeof(unsigned long long) * 16 * c->n_sms));
     }
     *ctx_out = c;
     return EFFORT_OK;
@@ -130,7 +130,7 @@ extern "C" int effort_debug_read_trace(effort_ctx_t* c, unsigned long long* host
     if (!c || !c->trace || !host) return EFFORT_EINVAL;
     CK(cudaDeviceSynchronize());
     int n = c->n_sms < max_rows ? c->n_sms : max_rows;
-    CK(cudaMemcpy(host, c->trace, sizeof(unsigned long long) * 8 * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(host, c->trace, sizeof(unsigned long long) * 16 * n, cudaMemcpyDeviceToHost));
     return n;
 }
 
@@ -258,13 +258,55 @@ static int mul_variant() {
 
 static constexpr size_t kMaxSmem = 227 * 1024;
 
+struct MulCall {  // one problem of a launch group, host side
+    MulProblem pb;
+    float* out;
+    int accumulate;
+    uint32_t* n_selected_dev;
+};
+
+// One launch group: [fused select+MAC kernel over all problems] -> [integrate over all problems].
+// CTAs are dealt to the problems in proportion to their bucket bytes.
 template <int SLOTS, int VEC, int U, int NW>
-static int launch_fused(MulProblem pb, int n_cta, int out_dim, int accumulate, float* out,
-                        uint32_t* n_selected_dev, cudaStream_t stream) {
-    pb.g = make_geom<VEC>(pb.C, n_cta);
-    const int per_cta = (pb.in + pb.g.RS - 1) / pb.g.RS;
-    pb.list_cap = ((per_cta * pb.P) + 3) & ~3;
-    const size_t smem = MulSmem<SLOTS, VEC, NW>::bytes(pb.list_cap);
+static int launch_fused_batch(MulCall* calls, int n, int n_cta, cudaStream_t stream) {
+    if (n < 1 || n > kMulBatchMax) return EFFORT_EINVAL;
+    MulBatch batch{};
+    IntegrateBatch ib{};
+    batch.n = n; ib.n = n;
+    double total_bytes = 0;
+    int cs_sum = 0;
+    for (int k = 0; k < n; k++) {
+        total_bytes += (double)calls[k].pb.in * calls[k].pb.C;
+        cs_sum += make_geom<VEC>(calls[k].pb.C, n_cta).CS;
+    }
+    if (cs_sum > n_cta) return EFFORT_ESHAPE;
+    int list_cap = 0, cta = 0, max_words = 0;
+    constexpr int TF = SLOTS * 32 * VEC;
+    for (int k = 0; k < n; k++) {
+        MulProblem& pb = calls[k].pb;
+        MulGeom g = make_geom<VEC>(pb.C, n_cta);
+        const double share = (double)pb.in * pb.C / total_bytes;
+        int rs = (int)((n_cta - (cs_sum - g.CS)) * share / g.CS);  // leave at least one row split to the others
+        if (n == 1) rs = n_cta / g.CS;
+        if (rs < 1) rs = 1;
+        g.RS = rs;
+        pb.g = g;
+        const int per_cta = (pb.in + g.RS - 1) / g.RS;
+        const int cap = ((per_cta < NW * 32 ? per_cta : NW * 32) * pb.P + 3) & ~3;  // entries added per scan round
+        const int full = ((per_cta * pb.P) + 3) & ~3;
+        list_cap = full > list_cap ? full : list_cap;
+        (void)cap;
+        batch.cta_begin[k] = cta;
+        cta += g.CS * g.RS;
+        batch.p[k] = pb;
+        ib.it[k] = IntegrateItem{pb.partial, calls[k].out, pb.sel_counts, calls[k].n_selected_dev, g, pb.C,
+                                 calls[k].accumulate};
+        max_words = g.CS * TF > max_words ? g.CS * TF : max_words;
+    }
+    if (cta > n_cta) return EFFORT_ESHAPE;
+    batch.cta_begin[n] = cta;
+    for (int k = 0; k < n; k++) batch.p[k].list_cap = list_cap;
+    const size_t smem = MulSmem<SLOTS, VEC, NW>::bytes(list_cap);
     if (smem > kMaxSmem) return EFFORT_ESHAPE;
     static size_t configured = 0;
     if (smem > configured) {
@@ -272,14 +314,10 @@ static int launch_fused(MulProblem pb, int n_cta, int out_dim, int accumulate, f
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const int grid = pb.g.CS * pb.g.RS;
-    bucket_mul_fused_kernel<SLOTS, VEC, U, NW><<<grid, NW * 32, smem, stream>>>(pb);
+    bucket_mul_fused_kernel<SLOTS, VEC, U, NW><<<cta, NW * 32, smem, stream>>>(batch);
     LAUNCHED();
-    constexpr int TF = SLOTS * 32 * VEC;
-    integrate_kernel<SLOTS, VEC><<<(pb.g.CS * TF + 31) / 32, 256, 0, stream>>>(
-        pb.partial, pb.g, pb.C, accumulate, out, pb.sel_counts, n_selected_dev);
+    integrate_kernel<SLOTS, VEC><<<dim3((max_words + 31) / 32, n), 256, 0, stream>>>(ib);
     LAUNCHED();
-    (void)out_dim;
     return EFFORT_OK;
 }
 
@@ -289,11 +327,10 @@ static size_t partial_floats(const effort_ctx* ctx, const effort_weights* w) {
     return (size_t)ctx->n_sms * slots * 32 * 8;
 }
 
-// One fused bucketMul: [fused select+MAC kernel] -> [integrate].  slot = scratch slot inside a batch.
-static int enqueue_bucket_mul(effort_ctx* ctx, const float* v, const effort_weights* w, const uint32_t* exp_no,
-                              float* out, double effort, int accumulate, int slot, size_t partial_off,
-                              cudaStream_t stream) {
-    MulProblem pb{};
+static MulCall make_call(effort_ctx* ctx, const float* v, const effort_weights* w, const uint32_t* exp_no,
+                         float* out, double effort, int accumulate, int slot, size_t partial_off) {
+    MulCall c{};
+    MulProblem& pb = c.pb;
     pb.v = v; pb.st16 = w->st16; pb.st32 = w->st32; pb.bk = w->fast_bk(); pb.probes = w->probes;
     pb.exp_no = exp_no; pb.cutoff_in = nullptr;
     pb.partial = ctx->partial + partial_off;
@@ -303,16 +340,28 @@ static int enqueue_bucket_mul(effort_ctx* ctx, const float* v, const effort_weig
     pb.q = effort_q(effort, w->n_probes);
     pb.layout = w->layout;
     pb.trace = ctx->trace;
-    uint32_t* nsel = ctx->sizes + 3 + slot;
-    if (w->kind == EFFORT_KIND_FP16) {
-        const int variant = (w->C % 8) ? 0 : mul_variant();  // 16-byte loads need C % 8 == 0
+    c.out = out; c.accumulate = accumulate; c.n_selected_dev = ctx->sizes + 3 + slot;
+    return c;
+}
+
+static int launch_calls(effort_ctx* ctx, MulCall* calls, int n, int kind, bool all_c8, cudaStream_t stream) {
+    if (kind == EFFORT_KIND_FP16) {
+        const int variant = all_c8 ? mul_variant() : 0;  // 16-byte loads need C % 8 == 0
         switch (variant) {
-            case 1: return launch_fused<16, 4, 16, 16>(pb, ctx->n_sms, w->out, accumulate, out, nsel, stream);
-            case 2: return launch_fused<16, 8, 8, 10>(pb, ctx->n_sms, w->out, accumulate, out, nsel, stream);
-            default: return launch_fused<16, 4, 8, 16>(pb, ctx->n_sms, w->out, accumulate, out, nsel, stream);
+            case 1: return launch_fused_batch<16, 4, 16, 16>(calls, n, ctx->n_sms, stream);
+            case 2: return launch_fused_batch<16, 8, 8, 10>(calls, n, ctx->n_sms, stream);
+            default: return launch_fused_batch<16, 4, 8, 16>(calls, n, ctx->n_sms, stream);
         }
     }
-    return launch_fused<32, 2, 8, 16>(pb, ctx->n_sms, w->out, accumulate, out, nsel, stream);
+    return launch_fused_batch<32, 2, 8, 16>(calls, n, ctx->n_sms, stream);
+}
+
+// One fused bucketMul.  slot = scratch slot inside a batch.
+static int enqueue_bucket_mul(effort_ctx* ctx, const float* v, const effort_weights* w, const uint32_t* exp_no,
+                              float* out, double effort, int accumulate, int slot, size_t partial_off,
+                              cudaStream_t stream) {
+    MulCall c = make_call(ctx, v, w, exp_no, out, effort, accumulate, slot, partial_off);
+    return launch_calls(ctx, &c, 1, w->kind, (w->C % 8) == 0, stream);
 }
 
 static int ensure_mul_scratch(effort_ctx* ctx, size_t partial_floats_needed, int slots) {
@@ -401,6 +450,7 @@ static int expert_mul_one(effort_ctx* ctx, const effort_mul_args_t& a, int slot,
 
 extern "C" int effort_expert_mul_batch(effort_ctx_t* ctx, const effort_mul_args_t* args, int n, void* stream_) {
     if (!ctx || !args || n <= 0 || n > kMaxBatch) return EFFORT_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
     size_t total = 0;
     for (int k = 0; k < n; k++) {
         int rc = check_mul_args(ctx, args[k].v_dev, args[k].w, args[k].out_dev, args[k].effort);
@@ -409,13 +459,31 @@ extern "C" int effort_expert_mul_batch(effort_ctx_t* ctx, const effort_mul_args_
     }
     int rc = ensure_mul_scratch(ctx, total, kMaxBatch);
     if (rc) return rc;
+    // FP16 problems with buckets loaded go into ONE launch group (up to kMulBatchMax); everything else
+    // (Q4: out.zero() + outliers; dense fallback) is enqueued one by one in order.
+    MulCall group[kMulBatchMax];
+    int ng = 0;
+    bool c8 = true;
     size_t off = 0;
+    auto flush = [&]() -> int {
+        if (!ng) return EFFORT_OK;
+        int r = launch_calls(ctx, group, ng, EFFORT_KIND_FP16, c8, stream);
+        ng = 0; c8 = true;
+        return r;
+    };
     for (int k = 0; k < n; k++) {
-        rc = expert_mul_one(ctx, args[k], k, off, (cudaStream_t)stream_);
-        if (rc) return rc;
-        off += partial_floats(ctx, args[k].w);
+        const effort_weights* w = args[k].w;
+        if (w->kind == EFFORT_KIND_FP16 && w->buckets) {
+            if (ng == kMulBatchMax && (rc = flush())) return rc;
+            group[ng++] = make_call(ctx, args[k].v_dev, w, args[k].exp_no_dev, args[k].out_dev, args[k].effort, 0, k, off);
+            c8 = c8 && (w->C % 8) == 0;
+        } else {
+            if ((rc = flush())) return rc;
+            if ((rc = expert_mul_one(ctx, args[k], k, off, stream))) return rc;
+        }
+        off += partial_floats(ctx, w);
     }
-    return EFFORT_OK;
+    return flush();
 }
 
 extern "C" int effort_expert_mul(effort_ctx_t* ctx, const float* v_dev, const effort_weights_t* w,
@@ -489,8 +557,10 @@ static int launch_dispatch_mac(effort_ctx* ctx, const effort_weights* w, float* 
         w->buckets, ctx->dispatch, ctx->sizes + 1, w->C, list_cap, g, ctx->partial);
     LAUNCHED();
     constexpr int TF = SLOTS * 32 * VEC;
-    integrate_kernel<SLOTS, VEC><<<(g.CS * TF + 31) / 32, 256, 0, stream>>>(
-        ctx->partial, g, w->C, w->kind == EFFORT_KIND_Q4 ? 1 : 0, out, nullptr, nullptr);
+    IntegrateBatch ib{};
+    ib.n = 1;
+    ib.it[0] = IntegrateItem{ctx->partial, out, nullptr, nullptr, g, w->C, w->kind == EFFORT_KIND_Q4 ? 1 : 0};
+    integrate_kernel<SLOTS, VEC><<<dim3((g.CS * TF + 31) / 32, 1), 256, 0, stream>>>(ib);
     LAUNCHED();
     return EFFORT_OK;
 }

@@ -244,8 +244,8 @@ def test_batch_equals_sequential(T, ops):
     ops.expertMulBatch([(v, w, None, o, 0.25) for w, o in zip(ws, outs_a)])
     for w, o in zip(ws, outs_b):
         ops.expertMul(v, w, None, o, 0.25)
-    for a, b in zip(outs_a, outs_b):
-        assert T.equal(a, b)
+    for a, b in zip(outs_a, outs_b):   # same selection; the CTA split (hence the fp32 order) differs
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= OUT_TOL
 
 
 def test_error_behaviour(T, ops):

@@ -23,19 +23,21 @@ L.effort_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 for k in range(200):
     ops.bucketMul(v, ws[k % 4], None, out, a.effort)
 torch.cuda.synchronize()
-names = ["start", "scored", "cutoff", "listed", "streamed", "partial"]
+names = ["start", "zeroed", "issued", "scored", "minmax", "phaseA", "cutoff", "masks", "listed", "streamed", "partial"]
 for rep in range(3):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     ops.bucketMul(v, ws[rep % 4], None, out, a.effort)
     e.record()
     torch.cuda.synchronize()
-    buf = np.zeros((148, 8), dtype=np.uint64)
+    buf = np.zeros((148, 16), dtype=np.uint64)
     n = L.effort_debug_read_trace(ctx._h, buf.ctypes.data, 148)
-    t = buf[:n, :6].astype(np.int64)
+    t = buf[:n, :11].astype(np.int64)
+    loops = buf[:n, 11:13]
     t = t[t[:, 0] > 0]
     t0 = t[:, 0].min()
     rel = (t - t0) / 1000.0
     print(f"{a.shape} effort {a.effort} rep {rep}: event total {s.elapsed_time(e)*1000:.1f} us; ctas {len(t)}")
+    print("   loops after phase A / total:", int(loops[0, 0]), int(loops[0, 1]))
     for k, nm in enumerate(names):
         print(f"   {nm:9s} min {rel[:,k].min():7.2f}  median {np.median(rel[:,k]):7.2f}  max {rel[:,k].max():7.2f} us")
