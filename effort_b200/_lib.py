@@ -14,7 +14,7 @@ vp, fp, u32p = C.c_void_p, C.c_void_p, C.c_void_p
 
 class MulArgs(C.Structure):
     _fields_ = [("v_dev", C.c_void_p), ("w", C.c_void_p), ("exp_no_dev", C.c_void_p),
-                ("out_dev", C.c_void_p), ("effort", C.c_double)]
+                ("out_dev", C.c_void_p), ("effort", C.c_double), ("v_cutoff_dev", C.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/effort_b200.h declares

@@ -58,6 +58,7 @@ __host__ __device__ inline MulGeom make_geom(int C, int n_cta) {
 
 struct MulProblem {
     const float* v;           // [in] fp32
+    const float* v_cut;       // first n_probes entries of the full input vector (== v unless row-sharded)
     const __half* st16;       // FP16 kind: one fp16 stat per row, same row order as `bk`
     const float* st32;        // Q4 kind:   one fp32 stat (avg) per row
     const uint16_t* bk;       // bucket rows [rows][C] 16-bit words
@@ -406,7 +407,7 @@ bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
     } else {
         constexpr int PER = (EFFORT_PROBES_MAX + NT - 1) / NT;
         float vals[PER];
-        score_probes(pb.v, pb.probes, e_no, pb.n_probes, vals, keep);
+        score_probes(pb.v_cut, pb.probes, e_no, pb.n_probes, vals, keep);
         EFFORT_TRACE(3);
         cutoff = block_bisect_cutoff(vals, pb.n_probes, pb.q, hdr.cut, nullptr,
                                      pb.trace ? pb.trace + (size_t)blockIdx.x * 16 : nullptr);

@@ -328,10 +328,11 @@ static size_t partial_floats(const effort_ctx* ctx, const effort_weights* w) {
 }
 
 static MulCall make_call(effort_ctx* ctx, const float* v, const effort_weights* w, const uint32_t* exp_no,
-                         float* out, double effort, int accumulate, int slot, size_t partial_off) {
+                         float* out, double effort, int accumulate, int slot, size_t partial_off,
+                         const float* v_cut = nullptr) {
     MulCall c{};
     MulProblem& pb = c.pb;
-    pb.v = v; pb.st16 = w->st16; pb.st32 = w->st32; pb.bk = w->fast_bk(); pb.probes = w->probes;
+    pb.v = v; pb.v_cut = v_cut ? v_cut : v; pb.st16 = w->st16; pb.st32 = w->st32; pb.bk = w->fast_bk(); pb.probes = w->probes;
     pb.exp_no = exp_no; pb.cutoff_in = nullptr;
     pb.partial = ctx->partial + partial_off;
     pb.sel_counts = ctx->sel_counts + (size_t)slot * ctx->n_sms;
@@ -475,7 +476,8 @@ extern "C" int effort_expert_mul_batch(effort_ctx_t* ctx, const effort_mul_args_
         const effort_weights* w = args[k].w;
         if (w->kind == EFFORT_KIND_FP16 && w->buckets) {
             if (ng == kMulBatchMax && (rc = flush())) return rc;
-            group[ng++] = make_call(ctx, args[k].v_dev, w, args[k].exp_no_dev, args[k].out_dev, args[k].effort, 0, k, off);
+            group[ng++] = make_call(ctx, args[k].v_dev, w, args[k].exp_no_dev, args[k].out_dev, args[k].effort, 0, k, off,
+                                    args[k].v_cutoff_dev);
             c8 = c8 && (w->C % 8) == 0;
         } else {
             if ((rc = flush())) return rc;
@@ -488,7 +490,7 @@ extern "C" int effort_expert_mul_batch(effort_ctx_t* ctx, const effort_mul_args_
 
 extern "C" int effort_expert_mul(effort_ctx_t* ctx, const float* v_dev, const effort_weights_t* w,
                                  const uint32_t* exp_no_dev, float* out_dev, double effort, void* stream_) {
-    effort_mul_args_t a{v_dev, w, exp_no_dev, out_dev, effort};
+    effort_mul_args_t a{v_dev, w, exp_no_dev, out_dev, effort, nullptr};
     return effort_expert_mul_batch(ctx, &a, 1, stream_);
 }
 
@@ -781,22 +783,22 @@ static int model_enqueue_token(effort_model* m, double effort, cudaStream_t s) {
         if (!l.wq) return EFFORT_ESTATE;
         add_rmsnorm_kernel<<<1, 1024, 0, s>>>(m->h, li ? m->ffn_out : nullptr, l.attn_norm, c.dim, c.norm_eps, m->h_norm);
         LAUNCHED();
-        effort_mul_args_t qkv[3] = {{m->h_norm, l.wq, nullptr, m->xq, effort},
-                                    {m->h_norm, l.wk, nullptr, m->xk, effort},
-                                    {m->h_norm, l.wv, nullptr, m->xv, effort}};
+        effort_mul_args_t qkv[3] = {{m->h_norm, l.wq, nullptr, m->xq, effort, nullptr},
+                                    {m->h_norm, l.wk, nullptr, m->xk, effort, nullptr},
+                                    {m->h_norm, l.wv, nullptr, m->xv, effort, nullptr}};
         if ((rc = effort_expert_mul_batch(ctx, qkv, 3, s))) return rc;
         attention_kernel<<<c.n_heads, 256, 0, s>>>(m->xq, m->xk, m->xv, l.kc, l.vc, m->pos, c.n_heads, c.n_kv_heads,
                                                    c.rope_theta, 0, m->attn);
         LAUNCHED();
-        effort_mul_args_t wo = {m->attn, l.wo, nullptr, m->attn_ffn_out, effort};
+        effort_mul_args_t wo = {m->attn, l.wo, nullptr, m->attn_ffn_out, effort, nullptr};
         if ((rc = effort_expert_mul_batch(ctx, &wo, 1, s))) return rc;
         add_rmsnorm_kernel<<<1, 1024, 0, s>>>(m->h, m->attn_ffn_out, l.ffn_norm, c.dim, c.norm_eps, m->fxn);
         LAUNCHED();
-        effort_mul_args_t w13[2] = {{m->fxn, l.w1, nullptr, m->x1, effort}, {m->fxn, l.w3, nullptr, m->x3, effort}};
+        effort_mul_args_t w13[2] = {{m->fxn, l.w1, nullptr, m->x1, effort, nullptr}, {m->fxn, l.w3, nullptr, m->x3, effort, nullptr}};
         if ((rc = effort_expert_mul_batch(ctx, w13, 2, s))) return rc;
         silu_mul_kernel<<<(c.hidden_dim + 255) / 256, 256, 0, s>>>(m->x1, m->x3, c.hidden_dim, m->x2);
         LAUNCHED();
-        effort_mul_args_t w2 = {m->x2, l.w2, nullptr, m->ffn_out, effort};
+        effort_mul_args_t w2 = {m->x2, l.w2, nullptr, m->ffn_out, effort, nullptr};
         if ((rc = effort_expert_mul_batch(ctx, &w2, 1, s))) return rc;
     }
     add_rmsnorm_kernel<<<1, 1024, 0, s>>>(m->h, m->ffn_out, m->norm, c.dim, c.norm_eps, m->out_normed);

@@ -168,13 +168,20 @@ def expertMul(v, by: ExpertWeights, expNo=None, out=None, effort: float = 0.25, 
 
 
 def expertMulBatch(calls: Sequence[tuple], ctx: Optional[Context] = None):
-    """calls: [(v, by, expNo, out, effort), ...] independent expertMuls enqueued as one launch group."""
+    """calls: [(v, by, expNo, out, effort[, vCutoff]), ...] independent expertMuls enqueued as one launch group.
+    vCutoff (tensor-parallel row shards only): the first 4096 entries of the full input vector."""
     ctx = ctx or default_context()
     arr = (MulArgs * len(calls))()
-    for k, (v, by, expNo, out, effort) in enumerate(calls):
+    for k, call in enumerate(calls):
+        v, by, expNo, out, effort = call[:5]
+        v_cut = call[5] if len(call) > 5 else None
         _check_vec(v, by.inSize, "v")
         _check_vec(out, by.outSize, "out")
-        arr[k] = MulArgs(v.data_ptr(), by._h, _ptr(expNo), out.data_ptr(), float(effort))
+        if v_cut is not None:
+            _need(v_cut, torch.float32, "vCutoff")
+            if v_cut.numel() < 4096:
+                raise EffortError("vCutoff must hold the first 4096 entries of the full input vector")
+        arr[k] = MulArgs(v.data_ptr(), by._h, _ptr(expNo), out.data_ptr(), float(effort), _ptr(v_cut))
     check(ctx._L.effort_expert_mul_batch(ctx._h, arr, len(calls), _stream_ptr()), "expertMulBatch")
 
 

@@ -115,6 +115,9 @@ typedef struct {
     const uint32_t* exp_no_dev;
     float* out_dev;
     double effort;
+    /* Tensor-parallel row shards only: the first 4096 entries of the FULL input vector,
+     * which findCutoff32 probes (bucketMul.metal:158-163), when v_dev is a rank-local slice.  NULL = v_dev. */
+    const float* v_cutoff_dev;
 } effort_mul_args_t;
 int effort_expert_mul_batch(effort_ctx_t* ctx, const effort_mul_args_t* args, int n, void* stream);
 

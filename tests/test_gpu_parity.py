@@ -394,3 +394,37 @@ def test_q4_routing_dense_fallback(T, ops):
     o2 = T.empty_like(out)
     ops.expertMul(dev(T, v), q4, None, o2, 1.0)
     assert O.cossim(o2.cpu().numpy(), want) > 0.9              # sign * row-average quantisation, 2 % outliers exact
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tensor-parallel shards on the real kernels (ranks simulated one after the other on one GPU)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [2, 8])
+def test_tp_shards_reproduce_unsharded(T, ops, world):
+    from effort_b200 import sharding
+    w, r = conv(4096, 4096)
+    v = make_v(4096)
+    full = O.bucket_mul(v, r["buckets"], r["bucket.stats"], r["probes"], 4096, 4096, 0.25)
+    vd = dev(T, v)
+    col = np.zeros(4096, np.float32)
+    row = np.zeros(4096, np.float64)
+    n_row = 0
+    for g in range(world):
+        sc = sharding.shard_columns(r, 4096, 4096, g, world)
+        ew = ops.ExpertWeights(dev(T, sc["buckets"]), dev(T, sc["bucket.stats"]), dev(T, sc["probes"]), inDim=4096,
+                               outDim=sc["out"])
+        out = T.empty(sc["out"], dtype=T.float32, device="cuda")
+        ops.expertMul(vd, ew, None, out, 0.25)
+        assert ops.lastSelected() == full["n_selected"]              # identical selection on every rank
+        col[sc["out_offset"]: sc["out_offset"] + sc["out"]] = out.cpu().numpy()
+        sr = sharding.shard_rows(r, 4096, 4096, g, world)
+        ewr = ops.ExpertWeights(dev(T, sr["buckets"]), dev(T, sr["bucket.stats"]), dev(T, sr["probes"]),
+                                inDim=sr["in"], outDim=4096)
+        outr = T.empty(4096, dtype=T.float32, device="cuda")
+        v_loc = dev(T, v[sr["in_offset"]: sr["in_offset"] + sr["in"]])
+        ops.expertMulBatch([(v_loc, ewr, None, outr, 0.25, vd)])     # cutoff from the full vector's first 4096 dims
+        n_row += ops.lastSelected()
+        row += outr.cpu().numpy().astype(np.float64)                 # the all-reduce
+    assert rel_err(col, full["out64"]) <= OUT_TOL
+    assert n_row == full["n_selected"]
+    assert rel_err(row, full["out64"]) <= OUT_TOL
