@@ -120,7 +120,10 @@ def run_reference(args, rank, world):
 def workload_config(args, world):
     return {"workload": "Mistral-7B FP16 single-stream decode, random-init, 32 layers, 1 token/step (BASELINE configs[1])",
             "effort": args.effort, "context": f"positions {args.warmup}..{args.warmup + args.steps}",
-            "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (TP sharding: round 2)",
+            "parallelism": "single GPU" if world == 1 else (
+                f"{world} independent replicas" if getattr(args, "replicas", False) else
+                f"tp{world}: q/k/v/w1/w3 column-sharded, wo/w2 row-sharded, NCCL all-gather(cutoff input)+all-reduce per "
+                f"row-parallel GEMV, vocab-sharded lm_head"),
             "l2": "14 GB of distinct weights per token >> 126 MB L2: no flush needed"}
 
 
@@ -135,12 +138,19 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from effort_b200 import ops
-    from effort_b200.model import DecodeModel, MistralConfig
+    from effort_b200.model import DecodeModel, MistralConfig, init_comm
     from tools.clocks import ClockSampler
 
+    tp = world > 1 and not args.replicas
+    if tp:
+        init_comm(ops.default_context(), rank, world)
+    streams_total = 1 if tp else world   # independent token streams in the job
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
-        model = DecodeModel.random_init(MistralConfig(n_layers=args.layers), seed=1234 + rank)
+        if tp:   # one model, column/row sharded over the ranks (same seed everywhere)
+            model = DecodeModel.random_init(MistralConfig(n_layers=args.layers), seed=1234, tp_rank=rank, tp_size=world)
+        else:
+            model = DecodeModel.random_init(MistralConfig(n_layers=args.layers), seed=1234 + rank)
         torch.cuda.synchronize()
 
         def barrier():
@@ -174,7 +184,7 @@ def run_ours(args, rank, local_rank, world):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        tok_s = args.steps * world / (ms / 1e3)
+        tok_s = args.steps * streams_total / (ms / 1e3)
 
         # end to end: host token in (pinned, H2D), next token + logits out (D2H) every step
         import numpy as np
@@ -192,7 +202,7 @@ def run_ours(args, rank, local_rank, world):
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_tok_s = args.steps * world / float(t.item())
+        e2e_tok_s = args.steps * streams_total / float(t.item())
 
         extras = {}
         if rank == 0 and not args.quick:
@@ -201,15 +211,16 @@ def run_ours(args, rank, local_rank, world):
                     continue
                 ms_e, _ = decode_device(eff, 3, max(8, args.steps // 4))
                 extras[str(eff)] = max(8, args.steps // 4) / (ms_e / 1e3)
-        extras[str(args.effort)] = tok_s / world
+        extras[str(args.effort)] = tok_s / streams_total
 
         # roofline of the dominant operator: bucketMul 4096 -> 14336 (w1/w3; 50 % of the bucket bytes with w2)
         roof = None
         if rank == 0:
             peak, peak_src = peaks()
             w1s = [L[4] for L in model.layers]            # 32 distinct 117 MB matrices: every launch reads HBM
-            v = torch.randn(4096, device="cuda", dtype=torch.float32)
-            out = torch.empty(14336, device="cuda", dtype=torch.float32)
+            r_in, r_out = w1s[0].inSize, w1s[0].outSize   # 4096 -> 14336 (/world under TP)
+            v = torch.randn(r_in, device="cuda", dtype=torch.float32)
+            out = torch.empty(r_out, device="cuda", dtype=torch.float32)
             for w in w1s[:4]:
                 ops.bucketMul(v, w, None, out, args.effort)
             torch.cuda.synchronize()
@@ -227,20 +238,20 @@ def run_ours(args, rank, local_rank, world):
             e1.record(stream)
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / (reps * len(w1s))
-            alg = args.effort * 4096 * 14336 * 2
+            alg = args.effort * r_in * r_out * 2
             ach = alg / us / 1e3
             traffic = None
             try:  # dram__bytes_read+write per launch of the fused kernel from the committed ncu --set full capture
                 tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-                traffic = tr.get(str(args.effort))
+                traffic = tr.get(str(args.effort)) if world == 1 else None
             except Exception:
                 pass
             roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "kernel": "bucketMul 4096->14336 (bucket_mul_fused_kernel + integrate_kernel)",
+                    "kernel": f"bucketMul {r_in}->{r_out} (bucket_mul_fused_kernel + integrate_kernel)",
                     "us_per_launch": us, "algorithmic_bytes": alg, "peak_source": peak_src}
 
         cpu = None
-        if rank == 0 and world == 1 and not args.no_cpu:
+        if rank == 0 and world == 1 and not args.no_cpu:  # CPU baseline on rank 0 at N=1 only
             r = cpu_layer_sample(args.effort, reps=1)
             cpu = {"value": 1.0 / (r["bucketmul_s"] * 32), "unit": "tok/s", "cores": r["threads"], "kind": "port",
                    "sample": r["sample"], "dense_gemv_tok_s": 1.0 / (r["dense_s"] * 32)}
@@ -251,14 +262,14 @@ def run_ours(args, rank, local_rank, world):
             line = {
                 "metric": f"{METRIC} {args.effort}", "value": tok_s, "unit": "tok/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "fp16 weights, f32 accumulate",
+                "scaling": "strong" if (tp or world == 1) else "weak", "vs_baseline": None, "dtype": "fp16 weights, f32 accumulate",
                 "data": "synthetic", "config": workload_config(args, world),
                 "e2e": {"value": e2e_tok_s, "unit": "tok/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4 + 4 * model.cfg.vocab},
                 "gpu_launches": int(launches),
                 "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
                 "roofline": roof, "cpu_baseline": cpu, "efforts": extras,
                 "token_roofline": {"bytes_per_token": bytes_tok, "tok_s_at_peak": peak * 1e9 / bytes_tok,
-                                   "frac": (tok_s / world) / (peak * 1e9 / bytes_tok)},
+                                   "frac": (tok_s / streams_total) / (peak * 1e9 / bytes_tok / (world if tp else 1))},
             }
             print(json.dumps(line), flush=True)
     if world > 1:
@@ -275,6 +286,7 @@ def main():
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--quick", action="store_true", help="skip the effort 1.0 / 0.5 extras")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas instead of tensor parallelism")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

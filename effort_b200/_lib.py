@@ -40,6 +40,11 @@ SIGNATURES = {
                                        C.POINTER(C.c_float), C.POINTER(C.c_int), vp]),
     "effort_bucketize": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp]),
     "effort_q4_bucketize": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "effort_comm_unique_id": (C.c_int, [vp]),
+    "effort_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+    "effort_comm_destroy": (C.c_int, [vp]),
+    "effort_comm_all_reduce": (C.c_int, [vp, vp, C.c_size_t, vp]),
+    "effort_comm_all_gather": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
     "effort_model_create": (C.c_int, [vp, vp, C.POINTER(C.c_void_p)]),
     "effort_model_destroy": (C.c_int, [vp]),
     "effort_model_set_layer": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

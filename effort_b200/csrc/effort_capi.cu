@@ -73,7 +73,9 @@ struct effort_ctx {
     size_t sel_cap = 0;
     bool have_dispatch = false;
     int dispatch_kind = 0;
-    unsigned long long* trace = nullptr;  // [n_sms][8] when EFFORT_TRACE=1
+    unsigned long long* trace = nullptr;  // [n_sms][16] when EFFORT_TRACE=1
+    void* comm = nullptr;                  // ncclComm_t
+    int comm_rank = 0, comm_world = 1;
 };
 
 static constexpr int kMaxBatch = 8;
@@ -637,6 +639,113 @@ extern "C" int effort_q4_bucketize(const void*, int, int, void*, void*, void*, v
 }
 
 // ---------------------------------------------------------------------------------------------------
+// tensor-parallel plumbing: NCCL resolved at run time
+// ---------------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+
+namespace {
+struct NcclUniqueId { char internal[128]; };
+typedef int (*nccl_get_unique_id_t)(NcclUniqueId*);
+typedef int (*nccl_comm_init_rank_t)(void**, int, NcclUniqueId, int);
+typedef int (*nccl_comm_destroy_t)(void*);
+typedef int (*nccl_all_reduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_all_gather_t)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef const char* (*nccl_get_error_string_t)(int);
+struct NcclApi {
+    nccl_get_unique_id_t get_unique_id = nullptr;
+    nccl_comm_init_rank_t comm_init_rank = nullptr;
+    nccl_comm_destroy_t comm_destroy = nullptr;
+    nccl_all_reduce_t all_reduce = nullptr;
+    nccl_all_gather_t all_gather = nullptr;
+    nccl_get_error_string_t get_error_string = nullptr;
+    bool ok = false;
+};
+constexpr int kNcclFloat = 7, kNcclSum = 0;
+
+NcclApi& nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* h = RTLD_DEFAULT;
+        if (!dlsym(h, "ncclAllReduce")) {
+            h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        }
+        if (h) {
+            api.get_unique_id = (nccl_get_unique_id_t)dlsym(h, "ncclGetUniqueId");
+            api.comm_init_rank = (nccl_comm_init_rank_t)dlsym(h, "ncclCommInitRank");
+            api.comm_destroy = (nccl_comm_destroy_t)dlsym(h, "ncclCommDestroy");
+            api.all_reduce = (nccl_all_reduce_t)dlsym(h, "ncclAllReduce");
+            api.all_gather = (nccl_all_gather_t)dlsym(h, "ncclAllGather");
+            api.get_error_string = (nccl_get_error_string_t)dlsym(h, "ncclGetErrorString");
+            api.ok = api.get_unique_id && api.comm_init_rank && api.comm_destroy && api.all_reduce && api.all_gather;
+        }
+    }
+    return api;
+}
+}  // namespace
+
+#define NK(expr)                                                                                  \
+    do {                                                                                          \
+        int _r = (expr);                                                                          \
+        if (_r != 0) {                                                                            \
+            g_cuda_err = std::string(#expr) + ": nccl error " + std::to_string(_r) +              \
+                         (nccl().get_error_string ? std::string(" ") + nccl().get_error_string(_r) : ""); \
+            return EFFORT_ECUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+extern "C" int effort_comm_unique_id(void* id128_out) {
+    if (!id128_out) return EFFORT_EINVAL;
+    if (!nccl().ok) { g_cuda_err = "libnccl not available"; return EFFORT_ECUDA; }
+    NcclUniqueId id;
+    NK(nccl().get_unique_id(&id));
+    memcpy(id128_out, &id, sizeof(id));
+    return EFFORT_OK;
+}
+
+extern "C" int effort_comm_init(effort_ctx_t* ctx, const void* id128, int rank, int world) {
+    if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return EFFORT_EINVAL;
+    if (!nccl().ok) { g_cuda_err = "libnccl not available"; return EFFORT_ECUDA; }
+    if (ctx->comm) return EFFORT_ESTATE;
+    NcclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    CK(cudaSetDevice(ctx->device));
+    NK(nccl().comm_init_rank(&ctx->comm, world, id, rank));
+    ctx->comm_rank = rank; ctx->comm_world = world;
+    return EFFORT_OK;
+}
+
+extern "C" int effort_comm_destroy(effort_ctx_t* ctx) {
+    if (!ctx) return EFFORT_EINVAL;
+    if (ctx->comm) { nccl().comm_destroy(ctx->comm); ctx->comm = nullptr; }
+    ctx->comm_world = 1; ctx->comm_rank = 0;
+    return EFFORT_OK;
+}
+
+extern "C" int effort_comm_all_reduce(effort_ctx_t* ctx, float* buf_dev, size_t count, void* stream) {
+    if (!ctx || !buf_dev) return EFFORT_EINVAL;
+    if (ctx->comm_world == 1) return EFFORT_OK;
+    if (!ctx->comm) return EFFORT_ESTATE;
+    NK(nccl().all_reduce(buf_dev, buf_dev, count, kNcclFloat, kNcclSum, ctx->comm, (cudaStream_t)stream));
+    return EFFORT_OK;
+}
+
+extern "C" int effort_comm_all_gather(effort_ctx_t* ctx, const float* send_dev, float* recv_dev, size_t send_count,
+                                      void* stream) {
+    if (!ctx || !send_dev || !recv_dev) return EFFORT_EINVAL;
+    if (ctx->comm_world == 1) {
+        if (send_dev != recv_dev)
+            CK(cudaMemcpyAsync(recv_dev, send_dev, send_count * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return EFFORT_OK;
+    }
+    if (!ctx->comm) return EFFORT_ESTATE;
+    NK(nccl().all_gather(send_dev, recv_dev, send_count, kNcclFloat, ctx->comm, (cudaStream_t)stream));
+    return EFFORT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // decode loop (runNetwork.swift:68-316 mirror)
 // ---------------------------------------------------------------------------------------------------
 #include <map>
@@ -654,6 +763,7 @@ struct effort_model {
     };
     std::vector<Layer> layers;
     const __half *norm = nullptr, *out_core = nullptr, *emb = nullptr;
+    float *attn_full = nullptr, *x2_full = nullptr, *logits_local = nullptr;  // tensor-parallel gather buffers
     float *h = nullptr, *h_norm = nullptr, *xq = nullptr, *xk = nullptr, *xv = nullptr, *attn = nullptr,
           *attn_ffn_out = nullptr, *fxn = nullptr, *x1 = nullptr, *x3 = nullptr, *x2 = nullptr, *ffn_out = nullptr,
           *out_normed = nullptr, *logits = nullptr;
@@ -681,12 +791,17 @@ extern "C" int effort_model_create(effort_ctx_t* ctx, const effort_model_config_
     if (cfg->head_dim != 128 || cfg->n_heads * cfg->head_dim != cfg->dim) return EFFORT_ESHAPE;
     if (cfg->n_kv_heads <= 0 || cfg->n_heads % cfg->n_kv_heads) return EFFORT_EINVAL;
     if (cfg->n_layers <= 0 || cfg->max_seq <= 0 || cfg->vocab <= 0) return EFFORT_EINVAL;
-    if (cfg->tp_size != 1) return EFFORT_ESHAPE;  // sharded decode: see effort_b200/parallel (round 2)
+    const int G = cfg->tp_size < 1 ? 1 : cfg->tp_size;
+    if (G > 1) {
+        if (!ctx->comm || ctx->comm_world != G || ctx->comm_rank != cfg->tp_rank) return EFFORT_ESTATE;
+        if (cfg->n_kv_heads % G || cfg->hidden_dim % G || cfg->vocab % G || (cfg->hidden_dim / G) % 16) return EFFORT_ESHAPE;
+    }
     effort_model* m = new (std::nothrow) effort_model();
     if (!m) return EFFORT_ENOMEM;
     m->ctx = ctx; m->cfg = *cfg;
     m->layers.resize(cfg->n_layers);
-    const size_t kv = (size_t)cfg->max_seq * cfg->n_kv_heads * cfg->head_dim;
+    m->cfg.tp_size = G;
+    const size_t kv = (size_t)cfg->max_seq * (cfg->n_kv_heads / G) * cfg->head_dim;
     int rc = 0;
     for (auto& l : m->layers) {
         if ((rc = model_alloc(m, l.kc, kv))) return rc;
@@ -700,7 +815,9 @@ extern "C" int effort_model_create(effort_ctx_t* ctx, const effort_model_config_
         (rc = model_alloc(m, m->x1, cfg->hidden_dim)) || (rc = model_alloc(m, m->x3, cfg->hidden_dim)) ||
         (rc = model_alloc(m, m->x2, cfg->hidden_dim)) || (rc = model_alloc(m, m->ffn_out, cfg->dim)) ||
         (rc = model_alloc(m, m->out_normed, cfg->dim)) || (rc = model_alloc(m, m->logits, cfg->vocab)) ||
-        (rc = model_alloc(m, m->pos, 1)) || (rc = model_alloc(m, m->token, 1)) || (rc = model_alloc(m, m->next, 1)))
+        (rc = model_alloc(m, m->pos, 1)) || (rc = model_alloc(m, m->token, 1)) || (rc = model_alloc(m, m->next, 1)) ||
+        (rc = model_alloc(m, m->attn_full, cfg->dim)) || (rc = model_alloc(m, m->x2_full, cfg->hidden_dim)) ||
+        (rc = model_alloc(m, m->logits_local, cfg->vocab)))
         return rc;
     CK(cudaMallocHost(&m->h_token, sizeof(int)));
     CK(cudaMallocHost(&m->h_next, sizeof(int)));
@@ -726,10 +843,11 @@ extern "C" int effort_model_set_layer(effort_model_t* m, int layer, const effort
     if (!m || layer < 0 || layer >= m->cfg.n_layers) return EFFORT_EINVAL;
     if (!wq || !wk || !wv || !wo || !w1 || !w2 || !w3 || !attn_norm_dev || !ffn_norm_dev) return EFFORT_EINVAL;
     const auto& c = m->cfg;
+    const int G = c.tp_size;
     const int kvd = c.n_kv_heads * c.head_dim;
     auto ok = [](const effort_weights* w, int in, int out) { return w->in == in && w->out == out; };
-    if (!ok(wq, c.dim, c.dim) || !ok(wk, c.dim, kvd) || !ok(wv, c.dim, kvd) || !ok(wo, c.dim, c.dim) ||
-        !ok(w1, c.dim, c.hidden_dim) || !ok(w3, c.dim, c.hidden_dim) || !ok(w2, c.hidden_dim, c.dim))
+    if (!ok(wq, c.dim, c.dim / G) || !ok(wk, c.dim, kvd / G) || !ok(wv, c.dim, kvd / G) || !ok(wo, c.dim / G, c.dim) ||
+        !ok(w1, c.dim, c.hidden_dim / G) || !ok(w3, c.dim, c.hidden_dim / G) || !ok(w2, c.hidden_dim / G, c.dim))
         return EFFORT_ESHAPE;
     auto& l = m->layers[layer];
     l.wq = wq; l.wk = wk; l.wv = wv; l.wo = wo; l.w1 = w1; l.w2 = w2; l.w3 = w3;
@@ -770,10 +888,14 @@ extern "C" size_t effort_model_bucket_bytes(const effort_model_t* m) {
     return b;
 }
 
-// enqueue one token (no graph logic).  token lives in m->token (device).
+// enqueue one token (no graph logic).  token lives in m->token (device).  With tp_size = G > 1 this rank holds
+// heads [rank*32/G, ...) and hidden columns [rank*14336/G, ...): q/k/v/w1/w3 are column shards (no exchange),
+// wo/w2 are row shards: all-gather the first 4096 dims of their input (cutoff parity), all-reduce the output.
 static int model_enqueue_token(effort_model* m, double effort, cudaStream_t s) {
     const auto& c = m->cfg;
     effort_ctx* ctx = m->ctx;
+    const int G = c.tp_size;
+    const int dim_l = c.dim / G, hid_l = c.hidden_dim / G, heads_l = c.n_heads / G, kv_l = c.n_kv_heads / G;
     if (!m->norm) return EFFORT_ESTATE;
     embed_kernel<<<4, 1024, 0, s>>>(m->token, m->emb, c.dim, m->h);
     LAUNCHED();
@@ -787,23 +909,40 @@ static int model_enqueue_token(effort_model* m, double effort, cudaStream_t s) {
                                     {m->h_norm, l.wk, nullptr, m->xk, effort, nullptr},
                                     {m->h_norm, l.wv, nullptr, m->xv, effort, nullptr}};
         if ((rc = effort_expert_mul_batch(ctx, qkv, 3, s))) return rc;
-        attention_kernel<<<c.n_heads, 256, 0, s>>>(m->xq, m->xk, m->xv, l.kc, l.vc, m->pos, c.n_heads, c.n_kv_heads,
-                                                   c.rope_theta, 0, m->attn);
+        attention_kernel<<<heads_l, 256, 0, s>>>(m->xq, m->xk, m->xv, l.kc, l.vc, m->pos, heads_l, kv_l,
+                                                 c.rope_theta, 0, m->attn);
         LAUNCHED();
-        effort_mul_args_t wo = {m->attn, l.wo, nullptr, m->attn_ffn_out, effort, nullptr};
+        const float* wo_cut = nullptr;
+        if (G > 1) {
+            if ((rc = effort_comm_all_gather(ctx, m->attn, m->attn_full, dim_l, s))) return rc;
+            wo_cut = m->attn_full;
+        }
+        effort_mul_args_t wo = {m->attn, l.wo, nullptr, m->attn_ffn_out, effort, wo_cut};
         if ((rc = effort_expert_mul_batch(ctx, &wo, 1, s))) return rc;
+        if (G > 1 && (rc = effort_comm_all_reduce(ctx, m->attn_ffn_out, c.dim, s))) return rc;
         add_rmsnorm_kernel<<<1, 1024, 0, s>>>(m->h, m->attn_ffn_out, l.ffn_norm, c.dim, c.norm_eps, m->fxn);
         LAUNCHED();
         effort_mul_args_t w13[2] = {{m->fxn, l.w1, nullptr, m->x1, effort, nullptr}, {m->fxn, l.w3, nullptr, m->x3, effort, nullptr}};
         if ((rc = effort_expert_mul_batch(ctx, w13, 2, s))) return rc;
-        silu_mul_kernel<<<(c.hidden_dim + 255) / 256, 256, 0, s>>>(m->x1, m->x3, c.hidden_dim, m->x2);
+        silu_mul_kernel<<<(hid_l + 255) / 256, 256, 0, s>>>(m->x1, m->x3, hid_l, m->x2);
         LAUNCHED();
-        effort_mul_args_t w2 = {m->x2, l.w2, nullptr, m->ffn_out, effort, nullptr};
+        const float* w2_cut = nullptr;
+        if (G > 1) {
+            if ((rc = effort_comm_all_gather(ctx, m->x2, m->x2_full, hid_l, s))) return rc;
+            w2_cut = m->x2_full;
+        }
+        effort_mul_args_t w2 = {m->x2, l.w2, nullptr, m->ffn_out, effort, w2_cut};
         if ((rc = effort_expert_mul_batch(ctx, &w2, 1, s))) return rc;
+        if (G > 1 && (rc = effort_comm_all_reduce(ctx, m->ffn_out, c.dim, s))) return rc;
     }
     add_rmsnorm_kernel<<<1, 1024, 0, s>>>(m->h, m->ffn_out, m->norm, c.dim, c.norm_eps, m->out_normed);
     LAUNCHED();
-    if ((rc = enqueue_basic_mul(m->out_normed, m->out_core, c.vocab, c.dim, m->logits, ctx->n_sms, s))) return rc;
+    if (G > 1) {  // vocab-sharded lm_head + all-gather of the logits
+        if ((rc = enqueue_basic_mul(m->out_normed, m->out_core, c.vocab / G, c.dim, m->logits_local, ctx->n_sms, s))) return rc;
+        if ((rc = effort_comm_all_gather(ctx, m->logits_local, m->logits, c.vocab / G, s))) return rc;
+    } else {
+        if ((rc = enqueue_basic_mul(m->out_normed, m->out_core, c.vocab, c.dim, m->logits, ctx->n_sms, s))) return rc;
+    }
     argmax_advance_kernel<<<1, 1024, 0, s>>>(m->logits, c.vocab, m->next, m->pos);
     LAUNCHED();
     return EFFORT_OK;

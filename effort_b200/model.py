@@ -16,8 +16,22 @@ from typing import Optional
 
 import torch
 
-from . import _lib, ops
+from . import _lib, ops, sharding
 from ._lib import ModelConfig, check
+
+
+def init_comm(ctx: "ops.Context", rank: int, world: int) -> None:
+    """Create the library's NCCL communicator for this process (one process per GPU).  The 128-byte id is made
+    by rank 0 and broadcast through the caller's torch.distributed group (plumbing only)."""
+    import torch.distributed as dist
+    L = _lib.load()
+    buf = (C.c_char * 128)()
+    if rank == 0:
+        check(L.effort_comm_unique_id(buf), "effort_comm_unique_id")
+    t = torch.frombuffer(bytearray(bytes(buf)), dtype=torch.uint8).cuda()
+    dist.broadcast(t, src=0)
+    raw = bytes(t.cpu().numpy().tobytes())
+    check(L.effort_comm_init(ctx._h, raw, rank, world), "effort_comm_init")
 
 
 @dataclass
@@ -39,12 +53,13 @@ def _rand_w(out_dim, in_dim, gen, scale=0.02):
 
 
 class DecodeModel:
-    def __init__(self, cfg: MistralConfig, ctx: Optional[ops.Context] = None):
+    def __init__(self, cfg: MistralConfig, ctx: Optional[ops.Context] = None, tp_rank: int = 0, tp_size: int = 1):
         self.cfg = cfg
         self.ctx = ctx or ops.default_context()
+        self.tp_rank, self.tp_size = tp_rank, tp_size
         self._L = _lib.load()
         c = ModelConfig(cfg.dim, cfg.hidden_dim, cfg.n_layers, cfg.n_heads, cfg.n_kv_heads, cfg.head_dim, cfg.vocab,
-                        cfg.max_seq, cfg.rope_theta, cfg.norm_eps, 0, 1)
+                        cfg.max_seq, cfg.rope_theta, cfg.norm_eps, tp_rank, tp_size)
         h = C.c_void_p()
         check(self._L.effort_model_create(self.ctx._h, C.byref(c), C.byref(h)), "effort_model_create")
         self._h = h
@@ -75,15 +90,22 @@ class DecodeModel:
 
     @classmethod
     def random_init(cls, cfg: MistralConfig = MistralConfig(), seed: int = 1234, keep_reference_layout: bool = False,
-                    ctx: Optional[ops.Context] = None, norm_jitter: float = 0.1) -> "DecodeModel":
-        """Random-init weights ~ N(0, 0.02^2), converted on the GPU (effort_bucketize)."""
-        m = cls(cfg, ctx)
+                    ctx: Optional[ops.Context] = None, norm_jitter: float = 0.1, tp_rank: int = 0,
+                    tp_size: int = 1) -> "DecodeModel":
+        """Random-init weights ~ N(0, 0.02^2), converted on the GPU (effort_bucketize).
+        With tp_size > 1 every rank draws the SAME full matrices (same seed), converts them and keeps its shard
+        (effort_b200/sharding.py): the sharded model computes what the unsharded one does."""
+        m = cls(cfg, ctx, tp_rank, tp_size)
         gen = torch.Generator(device="cuda").manual_seed(seed)
         kvd = cfg.n_kv_heads * cfg.head_dim
 
-        def make(out_dim, in_dim):
+        def make(out_dim, in_dim, mode="column"):
             w = _rand_w(out_dim, in_dim, gen)
             t = ops.bucketize(w)
+            if tp_size > 1:
+                fn = sharding.shard_columns if mode == "column" else sharding.shard_rows
+                t = fn(t, in_dim, out_dim, tp_rank, tp_size)
+                in_dim, out_dim = t["in"], t["out"]
             ew = ops.ExpertWeights(t["buckets"], t["bucket.stats"], t["probes"], inDim=in_dim, outDim=out_dim)
             if not keep_reference_layout:
                 ew.release_reference_layout()
@@ -93,10 +115,14 @@ class DecodeModel:
             return (1.0 + norm_jitter * torch.randn(cfg.dim, generator=gen, device="cuda")).half()
 
         for i in range(cfg.n_layers):
-            m.set_layer(i, make(cfg.dim, cfg.dim), make(kvd, cfg.dim), make(kvd, cfg.dim), make(cfg.dim, cfg.dim),
-                        make(cfg.hidden_dim, cfg.dim), make(cfg.dim, cfg.hidden_dim), make(cfg.hidden_dim, cfg.dim),
-                        norm_vec(), norm_vec())
-        m.set_head(norm_vec(), _rand_w(cfg.vocab, cfg.dim, gen), _rand_w(cfg.vocab, cfg.dim, gen, scale=1.0))
+            m.set_layer(i, make(cfg.dim, cfg.dim), make(kvd, cfg.dim), make(kvd, cfg.dim), make(cfg.dim, cfg.dim, "row"),
+                        make(cfg.hidden_dim, cfg.dim), make(cfg.dim, cfg.hidden_dim, "row"),
+                        make(cfg.hidden_dim, cfg.dim), norm_vec(), norm_vec())
+        out_core = _rand_w(cfg.vocab, cfg.dim, gen)
+        if tp_size > 1:
+            v0, v1 = cfg.vocab * tp_rank // tp_size, cfg.vocab * (tp_rank + 1) // tp_size
+            out_core = out_core[v0:v1].contiguous()
+        m.set_head(norm_vec(), out_core, _rand_w(cfg.vocab, cfg.dim, gen, scale=1.0))
         torch.cuda.synchronize()
         torch.cuda.empty_cache()
         return m

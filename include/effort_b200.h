@@ -155,6 +155,21 @@ int effort_bucketize(const void* w_dev, int out_dim, int in_dim, void* buckets_d
 int effort_q4_bucketize(const void* wT_dev, int in_dim, int out_dim, void* buckets_dev, void* stats_dev,
                         void* probes_dev, void* stream);
 
+/* ---- tensor-parallel plumbing ------------------------------------------------- */
+/*
+ * One process per GPU.  The collectives of the sharded decode loop (all-gather of the row-parallel GEMV's
+ * cutoff input, all-reduce of its partial output) are NCCL calls enqueued on the caller's stream from inside
+ * the library (so they can live in the token's CUDA graph).  libnccl is resolved at run time (the copy already
+ * loaded by the host process, else dlopen("libnccl.so.2")).  Rank 0 creates the 128-byte id and hands it to the
+ * other ranks through whatever transport the host has (a process-group broadcast in effort_b200/model.py).
+ */
+int effort_comm_unique_id(void* id128_out);
+int effort_comm_init(effort_ctx_t* ctx, const void* id128, int rank, int world);
+int effort_comm_destroy(effort_ctx_t* ctx);
+/* in-place sum all-reduce / all-gather of fp32 device buffers over the ctx communicator (test + building block) */
+int effort_comm_all_reduce(effort_ctx_t* ctx, float* buf_dev, size_t count, void* stream);
+int effort_comm_all_gather(effort_ctx_t* ctx, const float* send_dev, float* recv_dev, size_t send_count, void* stream);
+
 /* ---- decode loop (host orchestration of the callers either side of the path) ----------------------- */
 /*
  * runNetwork(tokens:effort:)  runNetwork.swift:68-316, one token per call: per layer rmsNormFast*attnNorm,
@@ -176,7 +191,11 @@ typedef struct {
     int max_seq;     /* maxSeqLen 2048 */
     float rope_theta;/* 1e6: freqs = 1e-6^(j/64), model.swift:701 */
     float norm_eps;  /* 1e-5, aux.metal:151 */
-    int tp_rank, tp_size; /* tensor-parallel shard of this process (1 = unsharded); see DESIGN.md section 6 */
+    int tp_rank, tp_size; /* tensor-parallel shard of this process (tp_size 1 = unsharded).  With tp_size = G > 1 the
+                             ctx must have a communicator (effort_comm_init) and the weights passed to
+                             effort_model_set_layer / set_head are this rank's shards: wq [dim -> dim/G],
+                             wk/wv [dim -> kv_dim/G], wo [dim/G -> dim] (row shard), w1/w3 [dim -> hidden/G],
+                             w2 [hidden/G -> dim] (row shard), output.core [vocab/G, dim]. */
 } effort_model_config_t;
 
 int effort_model_create(effort_ctx_t* ctx, const effort_model_config_t* cfg, effort_model_t** m_out);

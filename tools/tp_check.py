@@ -1,0 +1,54 @@
+"""Tensor-parallel decode check + timing, run under torchrun (one process per GPU):
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/tp_check.py
+Rank 0 also builds the unsharded model (same seed) and compares logits / greedy tokens."""
+import os, sys, time
+import numpy as np
+import torch
+import torch.distributed as dist
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from effort_b200 import ops  # noqa: E402
+from effort_b200.model import DecodeModel, MistralConfig, init_comm  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ctx = ops.default_context()
+init_comm(ctx, rank, world)
+layers = int(os.environ.get("TP_LAYERS", "2"))
+cfg = MistralConfig(n_layers=layers, vocab=4096, max_seq=64)
+stream = torch.cuda.Stream()
+with torch.cuda.stream(stream):
+    tp = DecodeModel.random_init(cfg, seed=7, tp_rank=rank, tp_size=world)
+    ref = DecodeModel.random_init(cfg, seed=7, ctx=ops.Context()) if rank == 0 else None
+    toks = [1, 17, 400, 999, 5, 23]
+    ok = True
+    for t in toks:
+        tok = torch.tensor([t], dtype=torch.int32, device="cuda")
+        tp.step(tok, 0.5)
+        torch.cuda.synchronize()
+        if rank == 0:
+            ref.step(tok, 0.5)
+            torch.cuda.synchronize()
+            a, b = tp.logits().cpu().numpy().astype(np.float64), ref.logits().cpu().numpy().astype(np.float64)
+            cs = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+            same = tp.next_token() == ref.next_token()
+            print(f"token {t}: cos-sim(tp, unsharded) = {cs:.7f}  next tokens equal: {same}", flush=True)
+            ok = ok and cs > 0.9995 and same
+    dist.barrier()
+    # timing of the sharded step (graph replay)
+    for _ in range(4):
+        tp.step(None, 0.25)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    n = 32
+    for _ in range(n):
+        tp.step(None, 0.25)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if rank == 0:
+        print(f"TP{world} {layers} layers: {e0.elapsed_time(e1) / n * 1e3:.1f} us/token; parity ok = {ok}", flush=True)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if (rank != 0 or ok) else 1)
