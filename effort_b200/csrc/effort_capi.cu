@@ -13,6 +13,7 @@
 #include "bucket_mul.cuh"
 #include "convert.cuh"
 #include "cutoff.cuh"
+#include "q4.cuh"
 
 using namespace effort;
 
@@ -634,8 +635,26 @@ extern "C" int effort_bucketize(const void* w_dev, int out_dim, int in_dim, void
     return EFFORT_OK;
 }
 
-extern "C" int effort_q4_bucketize(const void*, int, int, void*, void*, void*, void*) {
-    return EFFORT_ESHAPE;  // implemented in a later milestone (q4.cuh)
+extern "C" int effort_q4_bucketize(const void* wT_dev, int in_dim, int out_dim, void* buckets_dev, void* stats_dev,
+                                   void* probes_dev, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!wT_dev || !buckets_dev || !stats_dev || !probes_dev || in_dim <= 0 || out_dim <= 0) return EFFORT_EINVAL;
+    if (out_dim % 32) return EFFORT_EINVAL;  // 4 nibbles per word, q4_draft.py:305-312 asserts whole words
+    const size_t rows = (size_t)in_dim * 8;
+    const int n = out_dim / 8;
+    __half* absvals = nullptr;
+    CK(cudaMallocAsync(&absvals, rows * n * sizeof(__half), stream));
+    const size_t threads = (size_t)in_dim * (out_dim / 32);
+    q4_bucketize_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
+        (const uint16_t*)wT_dev, in_dim, out_dim, (uint16_t*)buckets_dev, (uint16_t*)absvals);
+    LAUNCHED();
+    q4_stats_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, stream>>>(absvals, rows, n, (float*)stats_dev);
+    LAUNCHED();
+    const int np = in_dim < out_dim ? in_dim : out_dim;
+    q4_probes_kernel<<<(np + 255) / 256, 256, 0, stream>>>((const uint16_t*)wT_dev, out_dim, np, (uint16_t*)probes_dev);
+    LAUNCHED();
+    CK(cudaFreeAsync(absvals, stream));
+    return EFFORT_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------
