@@ -344,6 +344,8 @@ bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
     const int lb = (int)blockIdx.x - batch.cta_begin[pi];  // CTA index inside the problem
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();
+    if (pb.exp_no) pdl_wait();  // the expert index may be produced by the previous kernel (MoE gate)
     const uint32_t e_no = pb.exp_no ? *pb.exp_no : 0u;
     const MulGeom g = pb.g;
     const int slice = lb % g.CS, rsp = lb / g.CS;
@@ -369,7 +371,6 @@ bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
         for (int rho = 0; rho < 16; rho++) sel_stat[k][rho] = 0.f;
         if (j < n_in) {
             const int i = rsp + j * g.RS;
-            sel_v[k] = pb.v[i];
             if constexpr (SLOTS == 16) {
                 if (pb.layout == kInputMajor && P == 16) {
                     const uint4* sp = reinterpret_cast<const uint4*>(pb.st16 + ((size_t)e_no * pb.in + i) * 16);
@@ -399,6 +400,13 @@ bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
         }
     }
 
+    // everything above read only constant weight metadata: under PDL it overlaps the previous kernel's tail.
+    pdl_wait();
+#pragma unroll
+    for (int k = 0; k < KSEL; k++) {
+        const int j = tid + k * NT;
+        if (j < n_in) sel_v[k] = pb.v[rsp + j * g.RS];
+    }
     EFFORT_TRACE(2);
     // 1. cutoff (every CTA redundantly: 24 KB of L2-resident inputs, no extra launch / global round trip)
     float cutoff;
@@ -569,6 +577,8 @@ integrate_kernel(const __grid_constant__ IntegrateBatch ib) {
     constexpr int TW = 32 * VEC;
     constexpr int TF = SLOTS * TW;
     __shared__ float red[8][32];
+    pdl_trigger();
+    pdl_wait();
     const IntegrateItem& it = ib.it[blockIdx.y];
     const MulGeom g = it.g;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

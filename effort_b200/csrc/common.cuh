@@ -49,6 +49,13 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
     return r;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute
+// may start while its predecessor still runs; everything that touches data the predecessor produces (or scratch it
+// still reads) must come after pdl_wait().  pdl_trigger() lets the successor start its independent prologue
+// (smem zeroing, loads of constant weight metadata) early.  Both are no-ops without the launch attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // L2 eviction policies: bucket rows are read once per token (evict_first) while the small per-matrix
 // metadata (stats, probes: ~41 MB for Mistral-7B) and the activations should stay L2 resident across the
 // 14 GB that stream through between two uses (evict_last).

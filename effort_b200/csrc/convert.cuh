@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(256)
 basic_mul_kernel(const float* __restrict__ v, const __half* __restrict__ W, int out, int in,
                  float* __restrict__ outv) {
     extern __shared__ float vs[];
+    pdl_trigger();
+    pdl_wait();
     for (int i = threadIdx.x; i < in; i += blockDim.x) vs[i] = __half2float(__float2half_rn(v[i]));
     __syncthreads();
     const int lane = threadIdx.x & 31;

@@ -10,6 +10,8 @@ namespace effort {
 // fetchRow16to32 (aux.metal:355-363): x = float(tok_embeddings[token])
 __global__ void embed_kernel(const int* __restrict__ token, const __half* __restrict__ emb, int dim,
                              float* __restrict__ x) {
+    pdl_trigger();
+    pdl_wait();
     const int t = *token;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += gridDim.x * blockDim.x)
         x[i] = __half2float(emb[(size_t)t * dim + i]);
@@ -23,6 +25,8 @@ add_rmsnorm_kernel(float* __restrict__ h, const float* __restrict__ add, const _
                    int dim, float eps, float* __restrict__ out) {
     __shared__ float red[32];
     __shared__ float total;
+    pdl_trigger();
+    pdl_wait();
     float ss = 0.f;
     for (int i = threadIdx.x; i < dim; i += blockDim.x) {
         float x = h[i];
@@ -51,6 +55,8 @@ __global__ void add_kernel(float* __restrict__ h, const float* __restrict__ add,
 // silu32b (matrix.metal:25-34): out = x3 * x1 / (1 + exp(-x1))
 __global__ void silu_mul_kernel(const float* __restrict__ x1, const float* __restrict__ x3, int n,
                                 float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = x3[i] * x1[i] / (1.f + expf(-x1[i]));
 }
@@ -73,6 +79,8 @@ attention_kernel(const float* __restrict__ xq, const float* __restrict__ xk, con
     __shared__ float acc_s[8][HD];
     __shared__ float sum_s[8];
     const int h = blockIdx.x, kvh = h / (n_heads / n_kv);
+    pdl_trigger();
+    pdl_wait();
     const int pos = *pos_dev;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     (void)tp_head0;
@@ -139,6 +147,8 @@ argmax_advance_kernel(const float* __restrict__ logits, int n, int* __restrict__
                       int* __restrict__ pos_dev) {
     __shared__ float bv[32];
     __shared__ int bi[32];
+    pdl_trigger();
+    pdl_wait();
     float best = -INFINITY;
     int idx = 0x7fffffff;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "bucket_mul.cuh"
@@ -143,6 +144,25 @@ extern "C" int effort_ctx_destroy(effort_ctx_t* c) {
     cudaFree(c->chunk_counts); cudaFree(c->partial); cudaFree(c->sel_counts);
     delete c;
     return EFFORT_OK;
+}
+
+// Launch with the programmatic-dependent-launch attribute (all kernels of the decode chain call pdl_wait()
+// before touching dependent data).  EFFORT_PDL=0 disables it (plain stream order).
+static bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EFFORT_PDL"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v == 1;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 template <typename T>
@@ -317,9 +337,9 @@ static int launch_fused_batch(MulCall* calls, int n, int n_cta, cudaStream_t str
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    bucket_mul_fused_kernel<SLOTS, VEC, U, NW><<<cta, NW * 32, smem, stream>>>(batch);
+    CK(launch_pdl(bucket_mul_fused_kernel<SLOTS, VEC, U, NW>, dim3(cta), dim3(NW * 32), smem, stream, batch));
     LAUNCHED();
-    integrate_kernel<SLOTS, VEC><<<dim3((max_words + 31) / 32, n), 256, 0, stream>>>(ib);
+    CK(launch_pdl(integrate_kernel<SLOTS, VEC>, dim3((max_words + 31) / 32, n), dim3(256), 0, stream, ib));
     LAUNCHED();
     return EFFORT_OK;
 }
@@ -422,7 +442,7 @@ static int enqueue_basic_mul(const float* v, const __half* core, int out_dim, in
     int grid = (out_dim + 7) / 8;
     const int max_grid = n_sms * 8;
     if (grid > max_grid) grid = max_grid;
-    basic_mul_kernel<<<grid, 256, smem, stream>>>(v, core, out_dim, in_dim, out);
+    CK(launch_pdl(basic_mul_kernel, dim3(grid), dim3(256), smem, stream, v, core, out_dim, in_dim, out));
     LAUNCHED();
     return EFFORT_OK;
 }
@@ -916,20 +936,21 @@ static int model_enqueue_token(effort_model* m, double effort, cudaStream_t s) {
     const int G = c.tp_size;
     const int dim_l = c.dim / G, hid_l = c.hidden_dim / G, heads_l = c.n_heads / G, kv_l = c.n_kv_heads / G;
     if (!m->norm) return EFFORT_ESTATE;
-    embed_kernel<<<4, 1024, 0, s>>>(m->token, m->emb, c.dim, m->h);
+    CK(launch_pdl(embed_kernel, dim3(4), dim3(1024), 0, s, (const int*)m->token, m->emb, c.dim, m->h));
     LAUNCHED();
     int rc;
     for (int li = 0; li < c.n_layers; li++) {
         auto& l = m->layers[li];
         if (!l.wq) return EFFORT_ESTATE;
-        add_rmsnorm_kernel<<<1, 1024, 0, s>>>(m->h, li ? m->ffn_out : nullptr, l.attn_norm, c.dim, c.norm_eps, m->h_norm);
+        CK(launch_pdl(add_rmsnorm_kernel, dim3(1), dim3(1024), 0, s, m->h, (const float*)(li ? m->ffn_out : nullptr),
+                      l.attn_norm, c.dim, c.norm_eps, m->h_norm));
         LAUNCHED();
         effort_mul_args_t qkv[3] = {{m->h_norm, l.wq, nullptr, m->xq, effort, nullptr},
                                     {m->h_norm, l.wk, nullptr, m->xk, effort, nullptr},
                                     {m->h_norm, l.wv, nullptr, m->xv, effort, nullptr}};
         if ((rc = effort_expert_mul_batch(ctx, qkv, 3, s))) return rc;
-        attention_kernel<<<heads_l, 256, 0, s>>>(m->xq, m->xk, m->xv, l.kc, l.vc, m->pos, heads_l, kv_l,
-                                                 c.rope_theta, 0, m->attn);
+        CK(launch_pdl(attention_kernel, dim3(heads_l), dim3(256), 0, s, (const float*)m->xq, (const float*)m->xk,
+                      (const float*)m->xv, l.kc, l.vc, (const int*)m->pos, heads_l, kv_l, c.rope_theta, 0, m->attn));
         LAUNCHED();
         const float* wo_cut = nullptr;
         if (G > 1) {
@@ -939,11 +960,13 @@ static int model_enqueue_token(effort_model* m, double effort, cudaStream_t s) {
         effort_mul_args_t wo = {m->attn, l.wo, nullptr, m->attn_ffn_out, effort, wo_cut};
         if ((rc = effort_expert_mul_batch(ctx, &wo, 1, s))) return rc;
         if (G > 1 && (rc = effort_comm_all_reduce(ctx, m->attn_ffn_out, c.dim, s))) return rc;
-        add_rmsnorm_kernel<<<1, 1024, 0, s>>>(m->h, m->attn_ffn_out, l.ffn_norm, c.dim, c.norm_eps, m->fxn);
+        CK(launch_pdl(add_rmsnorm_kernel, dim3(1), dim3(1024), 0, s, m->h, (const float*)m->attn_ffn_out, l.ffn_norm,
+                      c.dim, c.norm_eps, m->fxn));
         LAUNCHED();
         effort_mul_args_t w13[2] = {{m->fxn, l.w1, nullptr, m->x1, effort, nullptr}, {m->fxn, l.w3, nullptr, m->x3, effort, nullptr}};
         if ((rc = effort_expert_mul_batch(ctx, w13, 2, s))) return rc;
-        silu_mul_kernel<<<(hid_l + 255) / 256, 256, 0, s>>>(m->x1, m->x3, hid_l, m->x2);
+        CK(launch_pdl(silu_mul_kernel, dim3((hid_l + 255) / 256), dim3(256), 0, s, (const float*)m->x1,
+                      (const float*)m->x3, hid_l, m->x2));
         LAUNCHED();
         const float* w2_cut = nullptr;
         if (G > 1) {
@@ -954,7 +977,8 @@ static int model_enqueue_token(effort_model* m, double effort, cudaStream_t s) {
         if ((rc = effort_expert_mul_batch(ctx, &w2, 1, s))) return rc;
         if (G > 1 && (rc = effort_comm_all_reduce(ctx, m->ffn_out, c.dim, s))) return rc;
     }
-    add_rmsnorm_kernel<<<1, 1024, 0, s>>>(m->h, m->ffn_out, m->norm, c.dim, c.norm_eps, m->out_normed);
+    CK(launch_pdl(add_rmsnorm_kernel, dim3(1), dim3(1024), 0, s, m->h, (const float*)m->ffn_out, m->norm, c.dim,
+                  c.norm_eps, m->out_normed));
     LAUNCHED();
     if (G > 1) {  // vocab-sharded lm_head + all-gather of the logits
         if ((rc = enqueue_basic_mul(m->out_normed, m->out_core, c.vocab / G, c.dim, m->logits_local, ctx->n_sms, s))) return rc;
@@ -962,7 +986,7 @@ static int model_enqueue_token(effort_model* m, double effort, cudaStream_t s) {
     } else {
         if ((rc = enqueue_basic_mul(m->out_normed, m->out_core, c.vocab, c.dim, m->logits, ctx->n_sms, s))) return rc;
     }
-    argmax_advance_kernel<<<1, 1024, 0, s>>>(m->logits, c.vocab, m->next, m->pos);
+    CK(launch_pdl(argmax_advance_kernel, dim3(1), dim3(1024), 0, s, (const float*)m->logits, c.vocab, m->next, m->pos));
     LAUNCHED();
     return EFFORT_OK;
 }
