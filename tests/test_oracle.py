@@ -309,3 +309,43 @@ def test_basic_mul_casts_v_to_fp16():
     np.testing.assert_allclose(o64, want, rtol=1e-12)
     assert rel_err(o32, want) < 1e-5
     np.testing.assert_allclose(O.basic_mul_fast(v.astype(np.float16).astype(np.float32), w), want, rtol=2e-4, atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the derivation the CUDA cutoff relies on (csrc/cutoff.cuh, block_cutoff_direct): the literal bisection only ever
+# needs the capped count (k-3) + sum_{j=k-2..k+2} [T_j > b] of five order statistics
+# ---------------------------------------------------------------------------------------------------------
+def _direct_cutoff(vals, k):
+    f32 = np.float32
+    bf = lambda x: f32(O.lib().oracle_bf16_round(float(x)))
+    srt = np.sort(vals)[::-1]
+    T = [f32(np.inf) if r < 1 else (f32(-1) if r > len(vals) else srt[r - 1]) for r in range(k - 2, k + 3)]
+    mn, mx = bf(min(f32(999), vals.min())), bf(max(f32(-999), vals.max()))
+    nb, loops, min_c, max_c = f32((mn + mx) / f32(2)), 0, min(4096, k + 2), max(0, k - 3)
+    while True:
+        loops += 1
+        c = (k - 3) + sum(1 for t in T if t > nb)
+        if c < k:
+            mx, max_c = nb, c
+        else:
+            mn, min_c = nb, c
+        prev, nb = nb, f32((mx + mn) / f32(2))
+        if c == k or f32(mx - mn) < f32(0.00001) or abs(max_c - min_c) < 3 or loops > 100:
+            return nb, loops
+        if nb == prev:
+            return nb, 101
+
+
+def test_direct_order_statistic_replay_equals_literal_bisection(conv4096):
+    w, r = conv4096
+    rng = np.random.default_rng(0)
+    cases = [make_v(4096, s) for s in range(6)] + [
+        np.zeros(4096, np.float32), np.ones(4096, np.float32), make_v(4096, 3) * 1e4, make_v(4096, 4) * 1e-6,
+        np.eye(1, 4096, 17, dtype=np.float32)[0] * 5, np.round(make_v(4096, 9)), rng.integers(0, 3, 4096).astype(np.float32)]
+    with np.errstate(all="ignore"):
+        for v in cases:
+            vals = O.probe_vals(v, r["probes"])
+            for e in (1.0, 0.999, 0.9, 0.5, 0.25, 0.1, 0.001, 0.0):
+                c, loops = O.find_cutoff(v, r["probes"], e, return_loops=True)
+                c2, loops2 = _direct_cutoff(vals, 4096 - O.effort_to_q(e))
+                assert np.float32(c).view(np.uint32) == np.float32(c2).view(np.uint32) and loops == loops2, (e, c, c2)
