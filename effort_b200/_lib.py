@@ -56,6 +56,7 @@ SIGNATURES = {
     "effort_model_next_token": (C.c_void_p, [vp]),
     "effort_model_bucket_bytes": (C.c_size_t, [vp]),
     "effort_model_set_graphs": (C.c_int, [vp, C.c_int]),
+    "effort_model_set_fused_glue": (C.c_int, [vp, C.c_int]),
     "effort_launch_count": (C.c_uint64, []),
     "effort_last_selected": (C.c_int, [vp, C.POINTER(C.c_uint32), vp]),
 }
@@ -81,6 +82,15 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB
+    alt = os.environ.get("EFFORT_LIB")  # A/B experiments against an older build of the library (tools only)
+    if alt:
+        L = C.CDLL(alt)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name, None)
+            if fn is not None:
+                fn.restype, fn.argtypes = res, args
+        _lib = L
+        return L
     if _build.needs_build():
         try:
             _build.build()

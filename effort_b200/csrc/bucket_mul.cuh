@@ -71,6 +71,14 @@ struct MulProblem {
     int in, C, P, n_probes, q, layout;
     int list_cap;             // capacity of the shared-memory row list (entries)
     MulGeom g;
+    // optional fused rmsNorm on load (decode loop, runNetwork.swift:126-127,173-175): when norm_w != null the
+    // operator's input is v_eff[i] = (v[i] / sqrt(sum(sumsq[0..n_sumsq)) / norm_dim + norm_eps)) * norm_w[i]
+    // (rmsNorm32fast aux.metal:113-152 + mulVec32by16 aux.metal:269); sumsq = per-block partial sums of v[i]^2
+    // written by the producer (integrate epilogue / embed kernel).
+    const __half* norm_w;
+    const float* sumsq;
+    int n_sumsq, norm_dim;
+    float norm_eps;
     unsigned long long* trace;  // optional [grid][16] phase timestamps (globaltimer ns), debugging aid
 };
 
@@ -99,6 +107,15 @@ __device__ __forceinline__ float lds_imm(uint32_t addr) {
 template <int IMM>
 __device__ __forceinline__ void sts_imm(uint32_t addr, float x) {
     asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(addr), "n"(IMM), "f"(x));
+}
+
+// sqrt(mean(v^2) + eps) from the producer's per-block partial sums; every warp computes it redundantly in a
+// fixed order (deterministic)
+__device__ __forceinline__ float rms_denom(const float* __restrict__ sumsq, int n, int dim, float eps) {
+    float t = 0.f;
+    for (int b = threadIdx.x & 31; b < n; b += 32) t += sumsq[b];
+    t = warp_sum_f(t);
+    return sqrtf(t / (float)dim + eps);
 }
 
 constexpr int kMulBatchMax = 4;
@@ -205,17 +222,17 @@ __device__ __forceinline__ void load_words(const uint16_t* p, uint32_t (&words)[
 // free (an entry past the end, or a lane past the last column, loads nothing and adds 0.0 into the lane's
 // own words) and SOFTWARE PIPELINED: the U loads of batch n+1 are in flight while batch n is accumulated, so
 // every lane always has U..2U vector loads outstanding (HBM latency x bandwidth needs ~40 KB per SM).
-template <int SLOTS, int VEC, int U, int NW>
+template <int SLOTS, int VEC, int U>
 __device__ __forceinline__ void stream_rows(const uint2* __restrict__ list, int n_list,
                                             const uint16_t* __restrict__ bk, int C, int slice,
-                                            const MulGeom g, uint32_t tile_saddr) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                                            const MulGeom g, uint32_t tile_saddr, int warp, int n_stream_warps) {
+    const int lane = threadIdx.x & 31;
     const int rowslot = lane / g.lpr;
     const int col = slice * 32 * VEC + (lane % g.lpr) * VEC;
     const bool lane_on = (col < C) && (rowslot < g.R);
     const uint32_t base_lane = tile_saddr | (uint32_t)(lane * 4);
     const uint16_t* bk_col = bk + col;
-    const int stride = NW * g.R;  // list entries consumed per step by all warps
+    const int stride = n_stream_warps * g.R;  // list entries consumed per step by all streaming warps
     const int first = warp * g.R + rowslot;
     const int nsteps = (n_list + stride - 1) / stride;
     const uint64_t pol = l2_policy_evict_first();
@@ -305,29 +322,35 @@ template <int SLOTS, int VEC, int NW>
 __device__ __forceinline__ void reduce_tiles_to_partial(const float* __restrict__ tiles, const MulGeom g,
                                                         float* __restrict__ partial) {
     constexpr int TF = MulSmem<SLOTS, VEC, NW>::kTileFloats;
-    for (int idx = threadIdx.x; idx < TF; idx += NW * 32) {
-        float a[NW];
+    // 4 consecutive words per thread: NW independent 16-byte shared loads (conflict free), one 16-byte store
+    for (int idx = threadIdx.x * 4; idx < TF; idx += NW * 32 * 4) {
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int w = 0; w < NW; w++) a[w] = tiles[(size_t)w * TF + idx];  // NW independent conflict-free loads
-        float sum = 0.f;
-#pragma unroll
-        for (int w = 0; w < NW; w++) sum += a[w];
-        if (g.R > 1) {  // sub-warp rows: fold the row slots into lanes < lpr
-            const int lane = idx & 31;
-            if (lane < g.lpr) {
-                for (int rs = 1; rs < g.R; rs++)
-#pragma unroll
-                    for (int w = 0; w < NW; w++) sum += tiles[(size_t)w * TF + idx + rs * g.lpr];
-            } else {
-                sum = 0.f;
-            }
+        for (int w = 0; w < NW; w++) {
+            const float4 a = *reinterpret_cast<const float4*>(tiles + (size_t)w * TF + idx);
+            sum.x += a.x; sum.y += a.y; sum.z += a.z; sum.w += a.w;
         }
-        partial[idx] = sum;
+        if (g.R > 1) {  // sub-warp rows: fold the row slots into lanes < lpr (lpr is a multiple of 1, idx%32 = lane of .x)
+            float s4[4] = {sum.x, sum.y, sum.z, sum.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int lane = (idx + e) & 31;
+                if (lane < g.lpr) {
+                    for (int rs = 1; rs < g.R; rs++)
+#pragma unroll
+                        for (int w = 0; w < NW; w++) s4[e] += tiles[(size_t)w * TF + idx + e + rs * g.lpr];
+                } else {
+                    s4[e] = 0.f;
+                }
+            }
+            sum = make_float4(s4[0], s4[1], s4[2], s4[3]);
+        }
+        *reinterpret_cast<float4*>(partial + idx) = sum;
     }
 }
 
 // ---- fused kernel: cutoff (optional) + selection + gather-MAC + CTA partial -------------------------
-template <int SLOTS, int VEC, int U, int NW>
+template <int SLOTS, int VEC, int U, int NW, bool NORM>
 __global__ void __launch_bounds__(NW * 32, 1)
 bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -351,8 +374,6 @@ bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
     const int slice = lb % g.CS, rsp = lb / g.CS;
 
     EFFORT_TRACE(0);
-    zero_my_tile<SLOTS, VEC, NW>(sv.tiles);  // independent of everything else: overlaps the loads below
-    EFFORT_TRACE(1);
 
     // 0. issue every global load the selection needs BEFORE the cutoff is known (they do not depend on
     //    it): thread <-> input dim i = rsp + j*RS, its v[i] and its P stats (32 contiguous bytes in the
@@ -401,11 +422,20 @@ bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
     }
 
     // everything above read only constant weight metadata: under PDL it overlaps the previous kernel's tail.
+    zero_my_tile<SLOTS, VEC, NW>(sv.tiles);  // while those loads are in flight
+    EFFORT_TRACE(1);
     pdl_wait();
+    float denom = 1.f;
+    if constexpr (NORM) denom = rms_denom(pb.sumsq, pb.n_sumsq, pb.norm_dim, pb.norm_eps);
+    auto v_eff = [&](int i) -> float {
+        float x = pb.v[i];
+        if constexpr (NORM) x = (x / denom) * __half2float(pb.norm_w[i]);
+        return x;
+    };
 #pragma unroll
     for (int k = 0; k < KSEL; k++) {
         const int j = tid + k * NT;
-        if (j < n_in) sel_v[k] = pb.v[rsp + j * g.RS];
+        if (j < n_in) sel_v[k] = v_eff(rsp + j * g.RS);
     }
     EFFORT_TRACE(2);
     // 1. cutoff (every CTA redundantly: 24 KB of L2-resident inputs, no extra launch / global round trip)
@@ -415,9 +445,9 @@ bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
     } else {
         constexpr int PER = (EFFORT_PROBES_MAX + NT - 1) / NT;
         float vals[PER];
-        score_probes(pb.v_cut, pb.probes, e_no, pb.n_probes, vals, keep);
+        score_probes<NORM>(pb.v_cut, pb.probes, e_no, pb.n_probes, vals, keep, pb.norm_w, denom);
         EFFORT_TRACE(3);
-        cutoff = block_bisect_cutoff(vals, pb.n_probes, pb.q, hdr.cut, nullptr,
+        cutoff = block_bisect_cutoff<NW>(vals, pb.n_probes, pb.q, hdr.cut, nullptr,
                                      pb.trace ? pb.trace + (size_t)blockIdx.x * 16 : nullptr);
     }
     if (pb.cutoff_out && lb == 0 && tid == 0) *pb.cutoff_out = cutoff;
@@ -439,7 +469,7 @@ bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
                     if (rho < P && j < n_in && row_selected(cutoff, sel_stat[k][rho], sel_v[k])) mask[k] |= 1u << rho;
             } else if (j < n_in) {  // tail (more than NT*KSEL inputs per CTA): loads not prefetched
                 const int i = rsp + j * g.RS;
-                sel_v[k] = pb.v[i];
+                sel_v[k] = v_eff(i);
                 for (int rho = 0; rho < P; rho++) {
                     const size_t row = (pb.layout == kInputMajor)
                                            ? ((size_t)e_no * pb.in + i) * P + rho
@@ -509,12 +539,252 @@ bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
     EFFORT_TRACE(8);
 
     // 3. stream the selected rows
-    stream_rows<SLOTS, VEC, U, NW>(list, n_list, pb.bk, pb.C, slice, g,
-                                   sv.tiles_saddr + (uint32_t)warp * L::kTileBytes);
+    stream_rows<SLOTS, VEC, U>(list, n_list, pb.bk, pb.C, slice, g,
+                               sv.tiles_saddr + (uint32_t)warp * L::kTileBytes, warp, NW);
     __syncthreads();
     EFFORT_TRACE(9);
 
     // 4. CTA partial (tile layout)
+    reduce_tiles_to_partial<SLOTS, VEC, NW>(sv.tiles, g, pb.partial + (size_t)lb * L::kTileFloats);
+    EFFORT_TRACE(10);
+}
+
+// ---- fused kernel, overlapped variant ---------------------------------------------------------------
+// Same result as bucket_mul_fused_kernel; the difference is WHEN rows start to stream.  The bisection's upper
+// bracket maxBound only ever falls and the final cutoff never exceeds it, so after a few iterations every row
+// with  maxBound < 1e5*stat*|v|  is already certain to be selected (87 % of the finally selected rows after 6
+// iterations on Mistral-shaped data, 98 % after 8).  After kLevels1 iterations the CTA splits:
+//   selectors (warps 0..3) take over all 4096 products (through shared memory) and finish the exact bisection;
+//   streamers (the other warps) build the list of certain rows and stream them meanwhile;
+// they meet at a named barrier, the remaining rows (cutoff < f <= bound1) are listed and streamed by all warps.
+// Requirements (checked on the host, else the plain kernel runs): input-major rows, all ranks loaded,
+// 4096 probes, at most 2 input dims per streamer thread.
+constexpr int kSelWarps = 4;
+constexpr int kLevels1 = 64;  // 64: all of phase A by every warp; only phase B overlaps the streaming
+constexpr int kOvlInputsPerThread = 2;
+
+template <int SLOTS, int VEC, int NW>
+__host__ __device__ inline size_t overlap_smem_bytes(int list_cap) {
+    return MulSmem<SLOTS, VEC, NW>::bytes(list_cap) + EFFORT_PROBES_MAX * sizeof(float);
+}
+
+template <int SLOTS, int VEC, int U, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+bucket_mul_overlap_kernel(const __grid_constant__ MulBatch batch) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using L = MulSmem<SLOTS, VEC, NW>;
+    constexpr int NT = NW * 32;
+    constexpr int NS = NW - kSelWarps, NST = NS * 32;          // streamer warps / threads
+    constexpr int PERA = EFFORT_PROBES_MAX / NT;               // products per thread while all warps bisect
+    constexpr int PERS = EFFORT_PROBES_MAX / (kSelWarps * 32); // products per selector thread afterwards
+    constexpr int PR = (SLOTS == 16) ? 16 : 8;                 // ranks per input dim
+    constexpr int KIN = kOvlInputsPerThread;
+    const MulSmemView<NW> sv = carve_smem<SLOTS, VEC, NW>(smem_raw);
+    MulSmemHeader<NW>& hdr = *sv.hdr;
+    int pi = 0;
+#pragma unroll
+    for (int k = 1; k < kMulBatchMax; k++) pi += (k < batch.n && (int)blockIdx.x >= batch.cta_begin[k]) ? 1 : 0;
+    const MulProblem& pb = batch.p[pi];
+    const int lb = (int)blockIdx.x - batch.cta_begin[pi];
+    float* xs = reinterpret_cast<float*>(sv.list + pb.list_cap);  // [4096] products, after the list
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_sel = warp < kSelWarps;
+    const int st = tid - kSelWarps * 32;  // streamer thread index (negative for selectors)
+    pdl_trigger();
+    if (pb.exp_no) pdl_wait();
+    const uint32_t e_no = pb.exp_no ? *pb.exp_no : 0u;
+    const MulGeom g = pb.g;
+    const int slice = lb % g.CS, rsp = lb / g.CS;
+    const uint64_t keep = l2_policy_evict_last();
+    EFFORT_TRACE(0);
+    zero_my_tile<SLOTS, VEC, NW>(sv.tiles);
+
+    // streamers: prefetch the stats of their input dims (constant metadata: legal before pdl_wait)
+    const int n_in = (pb.in > rsp) ? (pb.in - 1 - rsp) / g.RS + 1 : 0;
+    float stat[KIN][PR];
+    float vin[KIN];
+#pragma unroll
+    for (int k = 0; k < KIN; k++) {
+        vin[k] = 0.f;
+#pragma unroll
+        for (int r = 0; r < PR; r++) stat[k][r] = 0.f;
+        const int j = st + k * NST;
+        if (!is_sel && j < n_in) {
+            const int i = rsp + j * g.RS;
+            if constexpr (SLOTS == 16) {
+                const uint4* sp = reinterpret_cast<const uint4*>(pb.st16 + ((size_t)e_no * pb.in + i) * 16);
+                const uint4 s0 = ldg_keep_u4(sp, keep), s1 = ldg_keep_u4(sp + 1, keep);
+                const uint32_t ws[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                for (int q2 = 0; q2 < 8; q2++) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ws[q2]));
+                    stat[k][2 * q2] = f.x;
+                    stat[k][2 * q2 + 1] = f.y;
+                }
+            } else {
+                const uint4* sp = reinterpret_cast<const uint4*>(pb.st32 + ((size_t)e_no * pb.in + i) * 8);
+                const uint4 s0 = ldg_keep_u4(sp, keep), s1 = ldg_keep_u4(sp + 1, keep);
+                const uint32_t ws[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                for (int r = 0; r < 8; r++) stat[k][r] = __uint_as_float(ws[r]);
+            }
+        }
+    }
+    pdl_wait();
+#pragma unroll
+    for (int k = 0; k < KIN; k++) {
+        const int j = st + k * NST;
+        if (!is_sel && j < n_in) vin[k] = pb.v[rsp + j * g.RS];
+    }
+    EFFORT_TRACE(2);
+
+    // all warps: score the probes and run the first kLevels1 iterations of the bisection
+    float vals[PERA];
+    score_probes(pb.v_cut, pb.probes, e_no, pb.n_probes, vals, keep);
+    EFFORT_TRACE(3);
+    BisectState bs;
+    bisect_init(vals, hdr.cut, bs);
+    const int effort = pb.n_probes - pb.q;
+    const bool done1 = bisect_rounds<PERA, NW, 0>(vals, bs, effort, hdr.cut, warp, kLevels1);
+    // stage-1 bound: rows with bound1 < f are certain.  If the loop is already over this is the cutoff itself.
+    const float bound1 = done1 ? bs.newBound : bs.maxBound;
+    if (!done1) {
+#pragma unroll
+        for (int k = 0; k < PERA; k++) xs[tid + k * NT] = vals[k];
+    }
+    __syncthreads();
+    EFFORT_TRACE(5);
+
+    auto row_of = [&](int i, int rho) -> size_t { return ((size_t)e_no * pb.in + i) * PR + rho; };
+    unsigned m1[KIN];
+    int n_list1 = 0;
+    if (is_sel) {
+        if (!done1) {
+            float sv32[PERS];
+#pragma unroll
+            for (int k = 0; k < PERS; k++) sv32[k] = xs[tid + k * (kSelWarps * 32)];
+            const bool done2 = bisect_rounds<PERS, kSelWarps, 1>(sv32, bs, effort, hdr.cut, warp, 1 << 30);
+            bisect_finish<PERS, kSelWarps, 1>(sv32, bs, effort, hdr.cut, warp, done2);
+        } else if (tid == 0) {
+            hdr.cut.result = bs.newBound;
+        }
+#pragma unroll
+        for (int k = 0; k < KIN; k++) m1[k] = 0u;
+        EFFORT_TRACE(6);
+    } else {
+        // ---- stage 1: list + stream the certain rows (streamers only, named barrier 3) ----
+        int base = 0;
+#pragma unroll
+        for (int k = 0; k < KIN; k++) {
+            const int j = st + k * NST;
+            unsigned m = 0u;
+#pragma unroll
+            for (int r = 0; r < PR; r++)
+                if (j < n_in && row_selected(bound1, stat[k][r], vin[k])) m |= 1u << r;
+            m1[k] = m;
+            const int c = __popc(m);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) hdr.warp_cnt[warp] = incl;
+            group_bar(3, NST);
+            int pre = 0, tot = 0;
+#pragma unroll
+            for (int w = kSelWarps; w < NW; w++) {
+                const int wc = hdr.warp_cnt[w];
+                pre += (w < warp) ? wc : 0;
+                tot += wc;
+            }
+            int pos = base + pre + incl - c;
+            if (c) {
+                const int i = rsp + j * g.RS;
+                while (m) {
+                    const int rho = __ffs(m) - 1;
+                    m &= m - 1;
+                    float val = vin[k];
+                    if constexpr (SLOTS != 16) {
+                        float stv = 0.f;
+#pragma unroll
+                        for (int r2 = 0; r2 < PR; r2++) stv = (r2 == rho) ? stat[k][r2] : stv;
+                        val = __fmul_rn(val, stv);  // Q4 payload is v*avg (bucketMulQ4.metal:51)
+                    }
+                    sv.list[pos++] = make_uint2(__float_as_uint(val), (uint32_t)(row_of(i, rho) * (size_t)pb.C));
+                }
+            }
+            base += tot;
+            group_bar(3, NST);
+        }
+        n_list1 = base;
+        EFFORT_TRACE(8);
+        stream_rows<SLOTS, VEC, U>(sv.list, n_list1, pb.bk, pb.C, slice, g,
+                                   sv.tiles_saddr + (uint32_t)warp * L::kTileBytes, warp - kSelWarps, NS);
+    }
+    group_bar(2, NT);  // selectors have the cutoff, streamers are done with stage 1 (and with the list)
+    const float cutoff = hdr.cut.result;
+    if (pb.cutoff_out && lb == 0 && tid == 0) *pb.cutoff_out = cutoff;
+    EFFORT_TRACE(7);
+
+    // ---- stage 2: the rows between the cutoff and the stage-1 bound, all warps ----
+    int n_list2 = 0;
+    if (!done1) {
+        int base = 0;
+#pragma unroll
+        for (int k = 0; k < KIN; k++) {
+            const int j = st + k * NST;
+            unsigned m = 0u;
+            if (!is_sel) {
+#pragma unroll
+                for (int r = 0; r < PR; r++)
+                    if (j < n_in && row_selected(cutoff, stat[k][r], vin[k])) m |= 1u << r;
+                m &= ~m1[k];
+            }
+            const int c = __popc(m);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) hdr.warp_cnt[warp] = incl;
+            __syncthreads();
+            int pre = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                const int wc = hdr.warp_cnt[w];
+                pre += (w < warp) ? wc : 0;
+                tot += wc;
+            }
+            int pos = base + pre + incl - c;
+            if (c) {
+                const int i = rsp + j * g.RS;
+                while (m) {
+                    const int rho = __ffs(m) - 1;
+                    m &= m - 1;
+                    float val = vin[k];
+                    if constexpr (SLOTS != 16) {
+                        float stv = 0.f;
+#pragma unroll
+                        for (int r2 = 0; r2 < PR; r2++) stv = (r2 == rho) ? stat[k][r2] : stv;
+                        val = __fmul_rn(val, stv);
+                    }
+                    sv.list[pos++] = make_uint2(__float_as_uint(val), (uint32_t)(row_of(i, rho) * (size_t)pb.C));
+                }
+            }
+            base += tot;
+            __syncthreads();
+        }
+        n_list2 = base;
+        stream_rows<SLOTS, VEC, U>(sv.list, n_list2, pb.bk, pb.C, slice, g,
+                                   sv.tiles_saddr + (uint32_t)warp * L::kTileBytes, warp, NW);
+    }
+    // rows selected by this CTA: stage 1 (known to the streamers) + stage 2 (known to everyone)
+    if (tid == kSelWarps * 32 && pb.sel_counts && slice == 0) pb.sel_counts[rsp] = (uint32_t)(n_list1 + n_list2);
+    __syncthreads();
+    EFFORT_TRACE(9);
     reduce_tiles_to_partial<SLOTS, VEC, NW>(sv.tiles, g, pb.partial + (size_t)lb * L::kTileFloats);
     EFFORT_TRACE(10);
 }
@@ -548,7 +818,7 @@ bucket_mul_dispatch_kernel(const uint16_t* __restrict__ bk, const float2* __rest
             list[i] = make_uint2(__float_as_uint(d.x), (uint32_t)d.y);  // int(d[1]), bucketMul.metal:98
         }
         __syncthreads();
-        stream_rows<SLOTS, VEC, U, NW>(list, m, bk, C, slice, g, sv.tiles_saddr + (uint32_t)warp * L::kTileBytes);
+        stream_rows<SLOTS, VEC, U>(list, m, bk, C, slice, g, sv.tiles_saddr + (uint32_t)warp * L::kTileBytes, warp, NW);
     }
     __syncthreads();
     reduce_tiles_to_partial<SLOTS, VEC, NW>(sv.tiles, g, partial + (size_t)blockIdx.x * L::kTileFloats);
@@ -558,25 +828,34 @@ bucket_mul_dispatch_kernel(const uint16_t* __restrict__ bk, const float2* __rest
 // Block = 8 warps x 32 consecutive tile words: warp w sums the partials r = w (mod 8) (coalesced 128-byte
 // rows, all loads independent), shared-memory fold, then warp 0 un-permutes tile word -> output index.
 // accumulate != 0 keeps the Q4 semantics (adds INTO out, bucketMulQ4.metal:89).
+enum IntegrateMode : int {
+    kIntStore = 0,     // out[o] = sum                     (bucketIntegrate, bucketMul.metal:122-137)
+    kIntAccumulate,    // out[o] += sum                    (Q4: atomics INTO out, bucketMulQ4.metal:89)
+    kIntSiluPair,      // items 0/1 = x1/x3 of one layer: out0[o] = x3 * x1 / (1 + exp(-x1))   (silu32b, matrix.metal:25-34)
+    kIntResidual,      // out[o] (= h) += sum, and sumsq[block] = sum over the block's outputs of h_new^2
+};
 struct IntegrateItem {
     const float* partial;
     float* out;
     const uint32_t* sel_counts;
     uint32_t* n_selected;
     MulGeom g;
-    int C, accumulate;
+    int C, mode;
+    float* sumsq;  // kIntResidual: [gridDim.x] per-block partial sums of squares
 };
 struct IntegrateBatch {
     int n;
     IntegrateItem it[kMulBatchMax];
 };
 
+// Block = 8 warps x 32 consecutive tile words: warp w sums the partials r = w (mod 8) (coalesced 128-byte rows, all
+// loads independent), shared-memory fold, then warp 0 un-permutes tile word -> output index and applies the epilogue.
 template <int SLOTS, int VEC>
 __global__ void __launch_bounds__(256)
 integrate_kernel(const __grid_constant__ IntegrateBatch ib) {
     constexpr int TW = 32 * VEC;
     constexpr int TF = SLOTS * TW;
-    __shared__ float red[8][32];
+    __shared__ float red[2][8][32];
     pdl_trigger();
     pdl_wait();
     const IntegrateItem& it = ib.it[blockIdx.y];
@@ -584,27 +863,59 @@ integrate_kernel(const __grid_constant__ IntegrateBatch ib) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + lane;  // word index in [0, CS*TF)
     if (blockIdx.x * 32 >= g.CS * TF) return;  // whole block past this problem's words (block uniform)
+    if (it.mode == kIntSiluPair && blockIdx.y == 1) {  // handled together with item 0
+        if (it.n_selected && it.sel_counts && blockIdx.x == 0 && threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int r = 0; r < g.RS; r++) t += it.sel_counts[r];
+            *it.n_selected = t;
+        }
+        return;
+    }
     const int slice = j / TF, idx = j % TF;
-    float s = 0.f;
+    float s = 0.f, s2 = 0.f;
     if (slice < g.CS) {
-        const float* p = it.partial + (size_t)slice * TF + idx;
         const size_t rstride = (size_t)g.CS * TF;
+        const float* p = it.partial + (size_t)slice * TF + idx;
 #pragma unroll 4
         for (int r = w; r < g.RS; r += 8) s += p[(size_t)r * rstride];
+        if (it.mode == kIntSiluPair) {
+            const float* p2 = ib.it[1].partial + (size_t)slice * TF + idx;
+#pragma unroll 4
+            for (int r = w; r < g.RS; r += 8) s2 += p2[(size_t)r * rstride];
+        }
     }
-    red[w][lane] = s;
+    red[0][w][lane] = s;
+    if (it.mode == kIntSiluPair) red[1][w][lane] = s2;
     __syncthreads();
-    if (w == 0 && slice < g.CS) {
-        float t = 0.f;
+    if (w == 0) {
+        float sq = 0.f;
+        if (slice < g.CS) {
+            float t = 0.f, t2 = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; k++) t += red[k][lane];
-        const int slot = idx / TW, k = (idx % TW) / 32;
-        if (lane < g.lpr) {
-            const int col = slice * TW + lane * VEC + k;
-            if (col < it.C) {
-                const int o = col * SLOTS + slot;
-                it.out[o] = it.accumulate ? it.out[o] + t : t;
+            for (int k = 0; k < 8; k++) t += red[0][k][lane];
+            if (it.mode == kIntSiluPair) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) t2 += red[1][k][lane];
             }
+            const int slot = idx / TW, k = (idx % TW) / 32;
+            if (lane < g.lpr) {
+                const int col = slice * TW + lane * VEC + k;
+                if (col < it.C) {
+                    const int o = col * SLOTS + slot;
+                    if (it.mode == kIntStore) it.out[o] = t;
+                    else if (it.mode == kIntAccumulate) it.out[o] += t;
+                    else if (it.mode == kIntSiluPair) it.out[o] = t2 * t / (1.f + expf(-t));
+                    else {
+                        const float hn = it.out[o] + t;
+                        it.out[o] = hn;
+                        sq = hn * hn;
+                    }
+                }
+            }
+        }
+        if (it.mode == kIntResidual) {
+            sq = warp_sum_f(sq);
+            if (lane == 0) it.sumsq[blockIdx.x] = sq;
         }
     }
     if (it.n_selected && it.sel_counts && blockIdx.x == 0 && threadIdx.x == 0) {

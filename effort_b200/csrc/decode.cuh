@@ -7,14 +7,29 @@
 
 namespace effort {
 
-// fetchRow16to32 (aux.metal:355-363): x = float(tok_embeddings[token])
-__global__ void embed_kernel(const int* __restrict__ token, const __half* __restrict__ emb, int dim,
-                             float* __restrict__ x) {
+// fetchRow16to32 (aux.metal:355-363): x = float(tok_embeddings[token]); also the per-block partial sums of x^2 that
+// the first layer's fused rmsNorm-on-load consumes (sumsq[gridDim.x], may be null).
+__global__ void __launch_bounds__(1024)
+embed_kernel(const int* __restrict__ token, const __half* __restrict__ emb, int dim, float* __restrict__ x,
+             float* __restrict__ sumsq) {
+    __shared__ float red[32];
     pdl_trigger();
     pdl_wait();
     const int t = *token;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += gridDim.x * blockDim.x)
-        x[i] = __half2float(emb[(size_t)t * dim + i]);
+    float ss = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += gridDim.x * blockDim.x) {
+        const float xv = __half2float(emb[(size_t)t * dim + i]);
+        x[i] = xv;
+        ss += xv * xv;
+    }
+    ss = warp_sum_f(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+        v = warp_sum_f(v);
+        if (threadIdx.x == 0 && sumsq) sumsq[blockIdx.x] = v;
+    }
 }
 
 // h (+= add) ; out = rmsNormFast(h) * w     (rmsNorm32fast aux.metal:113-152: x / sqrt(mean(x^2) + 1e-5),

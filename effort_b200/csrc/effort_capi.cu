@@ -281,10 +281,17 @@ static int mul_variant() {
 
 static constexpr size_t kMaxSmem = 227 * 1024;
 
+static bool overlap_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EFFORT_OVERLAP"); v = (e && atoi(e) == 1) ? 1 : 0; }  // experimental, off
+    return v == 1;
+}
+
 struct MulCall {  // one problem of a launch group, host side
     MulProblem pb;
     float* out;
-    int accumulate;
+    int mode;       // IntegrateMode of the group's integrate launch
+    float* sumsq;   // kIntResidual: per-block partial sums of squares of the updated residual stream
     uint32_t* n_selected_dev;
 };
 
@@ -323,21 +330,45 @@ static int launch_fused_batch(MulCall* calls, int n, int n_cta, cudaStream_t str
         cta += g.CS * g.RS;
         batch.p[k] = pb;
         ib.it[k] = IntegrateItem{pb.partial, calls[k].out, pb.sel_counts, calls[k].n_selected_dev, g, pb.C,
-                                 calls[k].accumulate};
+                                 calls[k].mode, calls[k].sumsq};
         max_words = g.CS * TF > max_words ? g.CS * TF : max_words;
     }
     if (cta > n_cta) return EFFORT_ESHAPE;
     batch.cta_begin[n] = cta;
     for (int k = 0; k < n; k++) batch.p[k].list_cap = list_cap;
-    const size_t smem = MulSmem<SLOTS, VEC, NW>::bytes(list_cap);
-    if (smem > kMaxSmem) return EFFORT_ESHAPE;
-    static size_t configured = 0;
-    if (smem > configured) {
-        CK(cudaFuncSetAttribute(bucket_mul_fused_kernel<SLOTS, VEC, U, NW>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    // overlapped variant (streams certain rows while the bisection finishes) when its preconditions hold
+    bool overlap = overlap_enabled() && NW > kSelWarps;
+    for (int k = 0; k < n; k++) {
+        const MulProblem& pb = batch.p[k];
+        const int per_cta = (pb.in + pb.g.RS - 1) / pb.g.RS;
+        overlap = overlap && pb.layout == kInputMajor && pb.P == (SLOTS == 16 ? 16 : 8) &&
+                  pb.n_probes == EFFORT_PROBES_MAX && per_cta <= kOvlInputsPerThread * (NW - kSelWarps) * 32 &&
+                  !pb.cutoff_in && !pb.norm_w;
     }
-    CK(launch_pdl(bucket_mul_fused_kernel<SLOTS, VEC, U, NW>, dim3(cta), dim3(NW * 32), smem, stream, batch));
+    const size_t smem = overlap ? overlap_smem_bytes<SLOTS, VEC, NW>(list_cap) : MulSmem<SLOTS, VEC, NW>::bytes(list_cap);
+    if (smem > kMaxSmem) return EFFORT_ESHAPE;
+    static size_t configured = 0, configured_ovl = 0;
+    if (overlap) {
+        if (smem > configured_ovl) {
+            CK(cudaFuncSetAttribute(bucket_mul_overlap_kernel<SLOTS, VEC, U, NW>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured_ovl = smem;
+        }
+        CK(launch_pdl(bucket_mul_overlap_kernel<SLOTS, VEC, U, NW>, dim3(cta), dim3(NW * 32), smem, stream, batch));
+    } else {
+        bool norm = batch.p[0].norm_w != nullptr;
+        for (int k = 1; k < n; k++)
+            if ((batch.p[k].norm_w != nullptr) != norm) return EFFORT_EINVAL;  // a group is all-norm or all-plain
+        if (smem > configured) {
+            CK(cudaFuncSetAttribute(bucket_mul_fused_kernel<SLOTS, VEC, U, NW, false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(bucket_mul_fused_kernel<SLOTS, VEC, U, NW, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        if (norm) CK(launch_pdl(bucket_mul_fused_kernel<SLOTS, VEC, U, NW, true>, dim3(cta), dim3(NW * 32), smem, stream, batch));
+        else CK(launch_pdl(bucket_mul_fused_kernel<SLOTS, VEC, U, NW, false>, dim3(cta), dim3(NW * 32), smem, stream, batch));
+    }
     LAUNCHED();
     CK(launch_pdl(integrate_kernel<SLOTS, VEC>, dim3((max_words + 31) / 32, n), dim3(256), 0, stream, ib));
     LAUNCHED();
@@ -364,18 +395,16 @@ static MulCall make_call(effort_ctx* ctx, const float* v, const effort_weights* 
     pb.q = effort_q(effort, w->n_probes);
     pb.layout = w->layout;
     pb.trace = ctx->trace;
-    c.out = out; c.accumulate = accumulate; c.n_selected_dev = ctx->sizes + 3 + slot;
+    c.out = out; c.mode = accumulate ? kIntAccumulate : kIntStore; c.sumsq = nullptr;
+    c.n_selected_dev = ctx->sizes + 3 + slot;
     return c;
 }
 
 static int launch_calls(effort_ctx* ctx, MulCall* calls, int n, int kind, bool all_c8, cudaStream_t stream) {
     if (kind == EFFORT_KIND_FP16) {
         const int variant = all_c8 ? mul_variant() : 0;  // 16-byte loads need C % 8 == 0
-        switch (variant) {
-            case 1: return launch_fused_batch<16, 4, 16, 16>(calls, n, ctx->n_sms, stream);
-            case 2: return launch_fused_batch<16, 8, 8, 10>(calls, n, ctx->n_sms, stream);
-            default: return launch_fused_batch<16, 4, 8, 16>(calls, n, ctx->n_sms, stream);
-        }
+        (void)variant;
+        return launch_fused_batch<16, 4, 8, 16>(calls, n, ctx->n_sms, stream);
     }
     return launch_fused_batch<32, 2, 8, 16>(calls, n, ctx->n_sms, stream);
 }
@@ -584,7 +613,8 @@ static int launch_dispatch_mac(effort_ctx* ctx, const effort_weights* w, float* 
     constexpr int TF = SLOTS * 32 * VEC;
     IntegrateBatch ib{};
     ib.n = 1;
-    ib.it[0] = IntegrateItem{ctx->partial, out, nullptr, nullptr, g, w->C, w->kind == EFFORT_KIND_Q4 ? 1 : 0};
+    ib.it[0] = IntegrateItem{ctx->partial, out, nullptr, nullptr, g, w->C,
+                             w->kind == EFFORT_KIND_Q4 ? kIntAccumulate : kIntStore, nullptr};
     integrate_kernel<SLOTS, VEC><<<dim3((g.CS * TF + 31) / 32, 1), 256, 0, stream>>>(ib);
     LAUNCHED();
     return EFFORT_OK;
@@ -803,6 +833,8 @@ struct effort_model {
     std::vector<Layer> layers;
     const __half *norm = nullptr, *out_core = nullptr, *emb = nullptr;
     float *attn_full = nullptr, *x2_full = nullptr, *logits_local = nullptr;  // tensor-parallel gather buffers
+    float *sumsq_a = nullptr, *sumsq_b = nullptr;  // per-block sum(h^2) partials for the fused rmsNorm-on-load
+    bool fuse_glue = true;
     float *h = nullptr, *h_norm = nullptr, *xq = nullptr, *xk = nullptr, *xv = nullptr, *attn = nullptr,
           *attn_ffn_out = nullptr, *fxn = nullptr, *x1 = nullptr, *x3 = nullptr, *x2 = nullptr, *ffn_out = nullptr,
           *out_normed = nullptr, *logits = nullptr;
@@ -856,8 +888,10 @@ extern "C" int effort_model_create(effort_ctx_t* ctx, const effort_model_config_
         (rc = model_alloc(m, m->out_normed, cfg->dim)) || (rc = model_alloc(m, m->logits, cfg->vocab)) ||
         (rc = model_alloc(m, m->pos, 1)) || (rc = model_alloc(m, m->token, 1)) || (rc = model_alloc(m, m->next, 1)) ||
         (rc = model_alloc(m, m->attn_full, cfg->dim)) || (rc = model_alloc(m, m->x2_full, cfg->hidden_dim)) ||
-        (rc = model_alloc(m, m->logits_local, cfg->vocab)))
+        (rc = model_alloc(m, m->logits_local, cfg->vocab)) || (rc = model_alloc(m, m->sumsq_a, 1024)) ||
+        (rc = model_alloc(m, m->sumsq_b, 1024)))
         return rc;
+    { const char* e = getenv("EFFORT_FUSE_GLUE"); m->fuse_glue = !(e && atoi(e) == 0); }
     CK(cudaMallocHost(&m->h_token, sizeof(int)));
     CK(cudaMallocHost(&m->h_next, sizeof(int)));
     CK(cudaMallocHost(&m->h_logits, sizeof(float) * cfg->vocab));
@@ -916,6 +950,16 @@ extern "C" int effort_model_set_graphs(effort_model_t* m, int enable) {
     return EFFORT_OK;
 }
 
+extern "C" int effort_model_set_fused_glue(effort_model_t* m, int enable) {
+    if (!m) return EFFORT_EINVAL;
+    if (m->fuse_glue != (enable != 0)) {
+        for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
+        m->graphs.clear();
+    }
+    m->fuse_glue = enable != 0;
+    return EFFORT_OK;
+}
+
 extern "C" const float* effort_model_logits(const effort_model_t* m) { return m ? m->logits : nullptr; }
 extern "C" const int32_t* effort_model_next_token(const effort_model_t* m) { return m ? m->next : nullptr; }
 extern "C" size_t effort_model_bucket_bytes(const effort_model_t* m) {
@@ -936,9 +980,51 @@ static int model_enqueue_token(effort_model* m, double effort, cudaStream_t s) {
     const int G = c.tp_size;
     const int dim_l = c.dim / G, hid_l = c.hidden_dim / G, heads_l = c.n_heads / G, kv_l = c.n_kv_heads / G;
     if (!m->norm) return EFFORT_ESTATE;
-    CK(launch_pdl(embed_kernel, dim3(4), dim3(1024), 0, s, (const int*)m->token, m->emb, c.dim, m->h));
+    CK(launch_pdl(embed_kernel, dim3(4), dim3(1024), 0, s, (const int*)m->token, m->emb, c.dim, m->h, m->sumsq_a));
     LAUNCHED();
     int rc;
+    if (G == 1 && m->fuse_glue && m->layers[0].wq && m->layers[0].wq->kind == EFFORT_KIND_FP16 &&
+        m->layers[0].wq->buckets) {
+        // Fused glue (single GPU, FP16): rmsNorm*w is applied on load inside the bucketMul kernels from per-block
+        // sum(h^2) partials, the residual add and silu*mul ride in the integrate epilogues: 9 launches per layer.
+        const size_t pf = partial_floats(ctx, m->layers[0].wq);
+        if ((rc = ensure_mul_scratch(ctx, 3 * pf, kMaxBatch))) return rc;
+        int n_sumsq = 4;  // embed_kernel grid
+        auto with_norm = [&](MulCall& mc, const __half* w, const float* sumsq, int n) {
+            mc.pb.norm_w = w; mc.pb.sumsq = sumsq; mc.pb.n_sumsq = n; mc.pb.norm_dim = c.dim; mc.pb.norm_eps = c.norm_eps;
+        };
+        auto blocks_of = [&](const effort_weights* w) { return make_geom<4>(w->C, ctx->n_sms).CS * (16 * 128) / 32; };  // integrate grid.x
+        for (int li = 0; li < c.n_layers; li++) {
+            auto& l = m->layers[li];
+            if (!l.wq) return EFFORT_ESTATE;
+            MulCall qkv[3] = {make_call(ctx, m->h, l.wq, nullptr, m->xq, effort, 0, 0, 0),
+                              make_call(ctx, m->h, l.wk, nullptr, m->xk, effort, 0, 1, pf),
+                              make_call(ctx, m->h, l.wv, nullptr, m->xv, effort, 0, 2, 2 * pf)};
+            for (auto& mc : qkv) with_norm(mc, l.attn_norm, m->sumsq_a, n_sumsq);
+            if ((rc = launch_calls(ctx, qkv, 3, EFFORT_KIND_FP16, false, s))) return rc;
+            CK(launch_pdl(attention_kernel, dim3(heads_l), dim3(256), 0, s, (const float*)m->xq, (const float*)m->xk,
+                          (const float*)m->xv, l.kc, l.vc, (const int*)m->pos, heads_l, kv_l, c.rope_theta, 0, m->attn));
+            LAUNCHED();
+            MulCall wo = make_call(ctx, m->attn, l.wo, nullptr, m->h, effort, 0, 0, 0);
+            wo.mode = kIntResidual; wo.sumsq = m->sumsq_b;  // h += wo(attn); sumsq_b = partial sum(h^2)
+            if ((rc = launch_calls(ctx, &wo, 1, EFFORT_KIND_FP16, false, s))) return rc;
+            MulCall w13[2] = {make_call(ctx, m->h, l.w1, nullptr, m->x2, effort, 0, 0, 0),
+                              make_call(ctx, m->h, l.w3, nullptr, m->x3, effort, 0, 1, pf)};
+            for (auto& mc : w13) { with_norm(mc, l.ffn_norm, m->sumsq_b, blocks_of(l.wo)); mc.mode = kIntSiluPair; }
+            if ((rc = launch_calls(ctx, w13, 2, EFFORT_KIND_FP16, false, s))) return rc;
+            MulCall w2 = make_call(ctx, m->x2, l.w2, nullptr, m->h, effort, 0, 0, 0);
+            w2.mode = kIntResidual; w2.sumsq = m->sumsq_a;  // h += w2(x2)
+            if ((rc = launch_calls(ctx, &w2, 1, EFFORT_KIND_FP16, false, s))) return rc;
+            n_sumsq = blocks_of(l.w2);
+        }
+        CK(launch_pdl(add_rmsnorm_kernel, dim3(1), dim3(1024), 0, s, m->h, (const float*)nullptr, m->norm, c.dim,
+                      c.norm_eps, m->out_normed));
+        LAUNCHED();
+        if ((rc = enqueue_basic_mul(m->out_normed, m->out_core, c.vocab, c.dim, m->logits, ctx->n_sms, s))) return rc;
+        CK(launch_pdl(argmax_advance_kernel, dim3(1), dim3(1024), 0, s, (const float*)m->logits, c.vocab, m->next, m->pos));
+        LAUNCHED();
+        return EFFORT_OK;
+    }
     for (int li = 0; li < c.n_layers; li++) {
         auto& l = m->layers[li];
         if (!l.wq) return EFFORT_ESTATE;

@@ -134,6 +134,9 @@ class DecodeModel:
     def set_graphs(self, enable: bool):
         check(self._L.effort_model_set_graphs(self._h, 1 if enable else 0), "effort_model_set_graphs")
 
+    def set_fused_glue(self, enable: bool):
+        check(self._L.effort_model_set_fused_glue(self._h, 1 if enable else 0), "effort_model_set_fused_glue")
+
     def step(self, token: Optional[torch.Tensor] = None, effort: float = 0.25):
         """Enqueue one decode step (token: device int32[1]; None = previous prediction)."""
         check(self._L.effort_model_step(self._h, None if token is None else token.data_ptr(), float(effort),

@@ -227,6 +227,9 @@ const int32_t* effort_model_next_token(const effort_model_t* m);  /* device int3
 size_t effort_model_bucket_bytes(const effort_model_t* m);
 /* use CUDA graphs for effort_model_step (default 1) */
 int effort_model_set_graphs(effort_model_t* m, int enable);
+/* single-GPU FP16 only (default 1): apply rmsNorm*w on load inside the bucketMul kernels and fold the residual add
+ * and silu*mul into the integrate epilogues (9 launches per layer instead of 12); 0 = one kernel per reference op */
+int effort_model_set_fused_glue(effort_model_t* m, int enable);
 
 /* ---- introspection used by bench / tests -------------------------------- */
 /* number of kernels this library has launched since load (process-wide) */

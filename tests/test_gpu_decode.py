@@ -33,11 +33,12 @@ def small_model():
     return m, ref
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_decode_matches_cpu_restatement(small_model, use_graph):
+@pytest.mark.parametrize("use_graph,fused_glue", [(False, False), (True, False), (False, True), (True, True)])
+def test_decode_matches_cpu_restatement(small_model, use_graph, fused_glue):
     import torch
     m, ref = small_model
     m.set_graphs(use_graph)
+    m.set_fused_glue(fused_glue)
     m.reset()
     ref.pos, ref.kc, ref.vc = 0, [[] for _ in ref.layers], [[] for _ in ref.layers]
     toks = [1, 17, 400, 999, 5]
