@@ -421,6 +421,9 @@ bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
         }
     }
 
+    constexpr int PER = (EFFORT_PROBES_MAX + NT - 1) / NT;
+    uint16_t prb[PER];
+    if (!pb.cutoff_in) load_probes(pb.probes, e_no, pb.n_probes, prb, keep);
     // everything above read only constant weight metadata: under PDL it overlaps the previous kernel's tail.
     zero_my_tile<SLOTS, VEC, NW>(sv.tiles);  // while those loads are in flight
     EFFORT_TRACE(1);
@@ -443,9 +446,8 @@ bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
     if (pb.cutoff_in) {
         cutoff = *pb.cutoff_in;
     } else {
-        constexpr int PER = (EFFORT_PROBES_MAX + NT - 1) / NT;
         float vals[PER];
-        score_probes<NORM>(pb.v_cut, pb.probes, e_no, pb.n_probes, vals, keep, pb.norm_w, denom);
+        score_loaded<NORM>(pb.v_cut, prb, pb.n_probes, vals, pb.norm_w, denom);
         EFFORT_TRACE(3);
         cutoff = block_bisect_cutoff<NW>(vals, pb.n_probes, pb.q, hdr.cut, nullptr,
                                      pb.trace ? pb.trace + (size_t)blockIdx.x * 16 : nullptr);

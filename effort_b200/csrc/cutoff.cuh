@@ -413,6 +413,34 @@ __device__ __forceinline__ void score_probes(const float* __restrict__ v, const 
     }
 }
 
+// Same in two halves so that the (constant) probes can be fetched before a PDL wait and the activations after.
+template <int PER>
+__device__ __forceinline__ void load_probes(const __half* __restrict__ probes, uint32_t exp_no, int n_probes,
+                                            uint16_t (&pr)[PER], uint64_t keep) {
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const int i = threadIdx.x + k * blockDim.x;
+        pr[k] = (i < n_probes) ? ldg_keep_u16(probes + (size_t)exp_no * n_probes + i, keep) : (uint16_t)0;
+    }
+}
+template <bool NORM = false, int PER>
+__device__ __forceinline__ void score_loaded(const float* __restrict__ v, const uint16_t (&pr)[PER], int n_probes,
+                                             float (&vals)[PER], const __half* __restrict__ norm_w = nullptr,
+                                             float denom = 1.f) {
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const int i = threadIdx.x + k * blockDim.x;
+        if (i < n_probes) {
+            const float p = bf16_round(__half2float(__ushort_as_half(pr[k])));
+            float vi = v[i];
+            if constexpr (NORM) vi = (vi / denom) * __half2float(norm_w[i]);
+            vals[k] = bf16_round(fabsf(__fmul_rn(__fmul_rn(kCutoffScale, vi), p)));
+        } else {
+            vals[k] = -1.f;
+        }
+    }
+}
+
 // Stand-alone launch (test hook effort_find_cutoff, and the first stage of the unfused path).
 __global__ void __launch_bounds__(kCutoffThreads, 1)
 find_cutoff_kernel(const float* __restrict__ v, const __half* __restrict__ probes,
