@@ -205,7 +205,7 @@ def run_ours(args, rank, local_rank, world):
         e2e_tok_s = args.steps * streams_total / float(t.item())
 
         extras = {}
-        if rank == 0 and not args.quick:
+        if not args.quick:   # every rank takes part: the sharded step holds collectives, and decode_device barriers
             for eff in (1.0, 0.5):
                 if abs(eff - args.effort) < 1e-9:
                     continue

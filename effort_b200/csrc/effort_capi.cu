@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "bucket_mul.cuh"
+#include "comm.cuh"
 #include "convert.cuh"
 #include "cutoff.cuh"
 #include "q4.cuh"
@@ -78,6 +79,9 @@ struct effort_ctx {
     unsigned long long* trace = nullptr;  // [n_sms][16] when EFFORT_TRACE=1
     void* comm = nullptr;                  // ncclComm_t
     int comm_rank = 0, comm_world = 1;
+    unsigned char* p2p_local = nullptr;    // this rank's symmetric buffer
+    void* p2p_peer[16] = {nullptr};        // mapped peers (own entry = p2p_local)
+    bool p2p_ready = false;
 };
 
 static constexpr int kMaxBatch = 8;
@@ -793,6 +797,64 @@ extern "C" int effort_comm_destroy(effort_ctx_t* ctx) {
     return EFFORT_OK;
 }
 
+// ---- one-shot NVLink collectives over CUDA-IPC mapped peer memory (comm.cuh) ----
+static bool p2p_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EFFORT_P2P"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v == 1;
+}
+
+extern "C" int effort_comm_p2p_local_handle(effort_ctx_t* ctx, void* handle64_out) {
+    if (!ctx || !handle64_out) return EFFORT_EINVAL;
+    if (!ctx->p2p_local) {
+        CK(cudaMalloc(&ctx->p2p_local, P2PLayout::total));
+        CK(cudaMemset(ctx->p2p_local, 0, P2PLayout::total));
+        CK(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->p2p_local));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64_out, &h, 64);
+    return EFFORT_OK;
+}
+
+extern "C" int effort_comm_p2p_connect(effort_ctx_t* ctx, const void* handles, int rank, int world) {
+    if (!ctx || !handles || !ctx->p2p_local || world < 1 || world > kP2PMaxRanks || rank < 0 || rank >= world)
+        return EFFORT_EINVAL;
+    for (int p = 0; p < world; p++) {
+        if (p == rank) { ctx->p2p_peer[p] = ctx->p2p_local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + 64 * p, 64);
+        CK(cudaIpcOpenMemHandle(&ctx->p2p_peer[p], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    ctx->comm_rank = rank; ctx->comm_world = world;
+    ctx->p2p_ready = true;
+    return EFFORT_OK;
+}
+
+template <int MODE>
+static int p2p_launch(effort_ctx* ctx, int site, const float* send, float* out, size_t count, cudaStream_t s) {
+    if (site < 0 || site >= kP2PSites || count * 8 * (size_t)ctx->comm_world > kP2PSiteBytes)  // 8-byte {value, seq} packets
+        return EFFORT_ESHAPE;
+    P2PArgs a{};
+    for (int p = 0; p < ctx->comm_world; p++) a.peer[p] = (unsigned char*)ctx->p2p_peer[p];
+    a.rank = ctx->comm_rank; a.world = ctx->comm_world; a.site = site;
+    CK(launch_pdl(p2p_collective_kernel<MODE>, dim3(kP2PBlocks), dim3(kP2PThreads), 0, s, a, send, out, (int)count));
+    LAUNCHED();
+    return EFFORT_OK;
+}
+
+// site-aware internal entry points: P2P when connected, else NCCL
+static int comm_all_reduce_site(effort_ctx* ctx, int site, float* buf, size_t count, cudaStream_t s) {
+    if (ctx->comm_world == 1) return EFFORT_OK;
+    if (ctx->p2p_ready && p2p_enabled()) return p2p_launch<1>(ctx, site, buf, buf, count, s);
+    return effort_comm_all_reduce(ctx, buf, count, s);
+}
+static int comm_all_gather_site(effort_ctx* ctx, int site, const float* send, float* recv, size_t count, cudaStream_t s) {
+    if (ctx->comm_world > 1 && ctx->p2p_ready && p2p_enabled()) return p2p_launch<0>(ctx, site, send, recv, count, s);
+    return effort_comm_all_gather(ctx, send, recv, count, s);
+}
+
 extern "C" int effort_comm_all_reduce(effort_ctx_t* ctx, float* buf_dev, size_t count, void* stream) {
     if (!ctx || !buf_dev) return EFFORT_EINVAL;
     if (ctx->comm_world == 1) return EFFORT_OK;
@@ -864,7 +926,7 @@ extern "C" int effort_model_create(effort_ctx_t* ctx, const effort_model_config_
     if (cfg->n_layers <= 0 || cfg->max_seq <= 0 || cfg->vocab <= 0) return EFFORT_EINVAL;
     const int G = cfg->tp_size < 1 ? 1 : cfg->tp_size;
     if (G > 1) {
-        if (!ctx->comm || ctx->comm_world != G || ctx->comm_rank != cfg->tp_rank) return EFFORT_ESTATE;
+        if ((!ctx->comm && !ctx->p2p_ready) || ctx->comm_world != G || ctx->comm_rank != cfg->tp_rank) return EFFORT_ESTATE;
         if (cfg->n_kv_heads % G || cfg->hidden_dim % G || cfg->vocab % G || (cfg->hidden_dim / G) % 16) return EFFORT_ESHAPE;
     }
     effort_model* m = new (std::nothrow) effort_model();
@@ -1025,12 +1087,23 @@ static int model_enqueue_token(effort_model* m, double effort, cudaStream_t s) {
         LAUNCHED();
         return EFFORT_OK;
     }
+    // tensor parallel with the one-shot NVLink collectives: the all-reduce of each row-parallel GEMV is fused with
+    // the residual add and the following rmsNorm*w, the x2 all-gather with silu*mul (csrc/comm.cuh)
+    const bool p2p = G > 1 && ctx->p2p_ready && p2p_enabled() && c.dim <= 4 * kP2PThreads && (size_t)c.hidden_dim * 8 <= kP2PSiteBytes;
+    auto p2p_args = [&](int site) {
+        P2PArgs a{};
+        for (int p = 0; p < G; p++) a.peer[p] = (unsigned char*)ctx->p2p_peer[p];
+        a.rank = ctx->comm_rank; a.world = G; a.site = site;
+        return a;
+    };
     for (int li = 0; li < c.n_layers; li++) {
         auto& l = m->layers[li];
         if (!l.wq) return EFFORT_ESTATE;
-        CK(launch_pdl(add_rmsnorm_kernel, dim3(1), dim3(1024), 0, s, m->h, (const float*)(li ? m->ffn_out : nullptr),
-                      l.attn_norm, c.dim, c.norm_eps, m->h_norm));
-        LAUNCHED();
+        if (!p2p || li == 0) {
+            CK(launch_pdl(add_rmsnorm_kernel, dim3(1), dim3(1024), 0, s, m->h, (const float*)((li && !p2p) ? m->ffn_out : nullptr),
+                          l.attn_norm, c.dim, c.norm_eps, m->h_norm));
+            LAUNCHED();
+        }  // else: h_norm was produced by the previous layer's fused all-reduce
         effort_mul_args_t qkv[3] = {{m->h_norm, l.wq, nullptr, m->xq, effort, nullptr},
                                     {m->h_norm, l.wk, nullptr, m->xk, effort, nullptr},
                                     {m->h_norm, l.wv, nullptr, m->xv, effort, nullptr}};
@@ -1040,35 +1113,56 @@ static int model_enqueue_token(effort_model* m, double effort, cudaStream_t s) {
         LAUNCHED();
         const float* wo_cut = nullptr;
         if (G > 1) {
-            if ((rc = effort_comm_all_gather(ctx, m->attn, m->attn_full, dim_l, s))) return rc;
+            if ((rc = comm_all_gather_site(ctx, 0, m->attn, m->attn_full, dim_l, s))) return rc;
             wo_cut = m->attn_full;
         }
         effort_mul_args_t wo = {m->attn, l.wo, nullptr, m->attn_ffn_out, effort, wo_cut};
         if ((rc = effort_expert_mul_batch(ctx, &wo, 1, s))) return rc;
-        if (G > 1 && (rc = effort_comm_all_reduce(ctx, m->attn_ffn_out, c.dim, s))) return rc;
-        CK(launch_pdl(add_rmsnorm_kernel, dim3(1), dim3(1024), 0, s, m->h, (const float*)m->attn_ffn_out, l.ffn_norm,
-                      c.dim, c.norm_eps, m->fxn));
-        LAUNCHED();
+        if (p2p) {
+            CK(launch_pdl(p2p_allreduce_residual_rmsnorm_kernel, dim3(1), dim3(kP2PThreads), 0, s, p2p_args(1),
+                          (const float*)m->attn_ffn_out, m->h, l.ffn_norm, c.dim, c.norm_eps, m->fxn));
+            LAUNCHED();
+        } else {
+            if (G > 1 && (rc = comm_all_reduce_site(ctx, 1, m->attn_ffn_out, c.dim, s))) return rc;
+            CK(launch_pdl(add_rmsnorm_kernel, dim3(1), dim3(1024), 0, s, m->h, (const float*)m->attn_ffn_out, l.ffn_norm,
+                          c.dim, c.norm_eps, m->fxn));
+            LAUNCHED();
+        }
         effort_mul_args_t w13[2] = {{m->fxn, l.w1, nullptr, m->x1, effort, nullptr}, {m->fxn, l.w3, nullptr, m->x3, effort, nullptr}};
         if ((rc = effort_expert_mul_batch(ctx, w13, 2, s))) return rc;
-        CK(launch_pdl(silu_mul_kernel, dim3((hid_l + 255) / 256), dim3(256), 0, s, (const float*)m->x1,
-                      (const float*)m->x3, hid_l, m->x2));
-        LAUNCHED();
         const float* w2_cut = nullptr;
-        if (G > 1) {
-            if ((rc = effort_comm_all_gather(ctx, m->x2, m->x2_full, hid_l, s))) return rc;
+        if (p2p) {
+            CK(launch_pdl(p2p_silu_allgather_kernel, dim3(1), dim3(kP2PThreads), 0, s, p2p_args(2), (const float*)m->x1,
+                          (const float*)m->x3, hid_l, m->x2, m->x2_full));
+            LAUNCHED();
             w2_cut = m->x2_full;
+        } else {
+            CK(launch_pdl(silu_mul_kernel, dim3((hid_l + 255) / 256), dim3(256), 0, s, (const float*)m->x1,
+                          (const float*)m->x3, hid_l, m->x2));
+            LAUNCHED();
+            if (G > 1) {
+                if ((rc = comm_all_gather_site(ctx, 2, m->x2, m->x2_full, hid_l, s))) return rc;
+                w2_cut = m->x2_full;
+            }
         }
         effort_mul_args_t w2 = {m->x2, l.w2, nullptr, m->ffn_out, effort, w2_cut};
         if ((rc = effort_expert_mul_batch(ctx, &w2, 1, s))) return rc;
-        if (G > 1 && (rc = effort_comm_all_reduce(ctx, m->ffn_out, c.dim, s))) return rc;
+        if (p2p) {  // h += all-reduce(ffn_out); the norm that follows is the next layer's attention norm or the final norm
+            const bool last = li + 1 == c.n_layers;
+            CK(launch_pdl(p2p_allreduce_residual_rmsnorm_kernel, dim3(1), dim3(kP2PThreads), 0, s, p2p_args(3),
+                          (const float*)m->ffn_out, m->h, last ? m->norm : m->layers[li + 1].attn_norm, c.dim, c.norm_eps,
+                          last ? m->out_normed : m->h_norm));
+            LAUNCHED();
+        } else if (G > 1 && (rc = comm_all_reduce_site(ctx, 3, m->ffn_out, c.dim, s))) return rc;
     }
-    CK(launch_pdl(add_rmsnorm_kernel, dim3(1), dim3(1024), 0, s, m->h, (const float*)m->ffn_out, m->norm, c.dim,
-                  c.norm_eps, m->out_normed));
-    LAUNCHED();
+    if (!p2p) {
+        CK(launch_pdl(add_rmsnorm_kernel, dim3(1), dim3(1024), 0, s, m->h, (const float*)m->ffn_out, m->norm, c.dim,
+                      c.norm_eps, m->out_normed));
+        LAUNCHED();
+    }
     if (G > 1) {  // vocab-sharded lm_head + all-gather of the logits
         if ((rc = enqueue_basic_mul(m->out_normed, m->out_core, c.vocab / G, c.dim, m->logits_local, ctx->n_sms, s))) return rc;
-        if ((rc = effort_comm_all_gather(ctx, m->logits_local, m->logits, c.vocab / G, s))) return rc;
+        if ((rc = comm_all_gather_site(ctx, 4, m->logits_local, m->logits, c.vocab / G, s))) return rc;
     } else {
         if ((rc = enqueue_basic_mul(m->out_normed, m->out_core, c.vocab, c.dim, m->logits, ctx->n_sms, s))) return rc;
     }

@@ -32,6 +32,17 @@ def init_comm(ctx: "ops.Context", rank: int, world: int) -> None:
     dist.broadcast(t, src=0)
     raw = bytes(t.cpu().numpy().tobytes())
     check(L.effort_comm_init(ctx._h, raw, rank, world), "effort_comm_init")
+    # one-shot NVLink collectives: exchange the CUDA-IPC handles of the symmetric buffers
+    import os
+    if os.environ.get("EFFORT_P2P", "1") != "0":
+        hb = (C.c_char * 64)()
+        check(L.effort_comm_p2p_local_handle(ctx._h, hb), "effort_comm_p2p_local_handle")
+        mine = torch.frombuffer(bytearray(bytes(hb)), dtype=torch.uint8).cuda()
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        blob = b"".join(bytes(x.cpu().numpy().tobytes()) for x in allh)
+        check(L.effort_comm_p2p_connect(ctx._h, blob, rank, world), "effort_comm_p2p_connect")
+        dist.barrier()
 
 
 @dataclass

@@ -166,6 +166,12 @@ int effort_q4_bucketize(const void* wT_dev, int in_dim, int out_dim, void* bucke
 int effort_comm_unique_id(void* id128_out);
 int effort_comm_init(effort_ctx_t* ctx, const void* id128, int rank, int world);
 int effort_comm_destroy(effort_ctx_t* ctx);
+/* One-shot NVLink collectives (csrc/comm.cuh): every rank maps every peer's symmetric buffer through CUDA IPC and a
+ * collective is one kernel per rank (peer stores + release flag + acquire spin), CUDA-graph replayable.  Used by the
+ * sharded decode loop when connected (EFFORT_P2P=0 forces NCCL).  local_handle: allocates this rank's buffer and
+ * returns its 64-byte cudaIpcMemHandle_t; connect: takes all ranks' handles (world x 64 bytes, rank order). */
+int effort_comm_p2p_local_handle(effort_ctx_t* ctx, void* handle64_out);
+int effort_comm_p2p_connect(effort_ctx_t* ctx, const void* handles, int rank, int world);
 /* in-place sum all-reduce / all-gather of fp32 device buffers over the ctx communicator (test + building block) */
 int effort_comm_all_reduce(effort_ctx_t* ctx, float* buf_dev, size_t count, void* stream);
 int effort_comm_all_gather(effort_ctx_t* ctx, const float* send_dev, float* recv_dev, size_t send_count, void* stream);
