@@ -124,6 +124,7 @@ constexpr int EFFORT_PROBES_MAX = 4096;  // probesCount (bucketMul.swift:19): th
 // CTAs [cta_begin[p], cta_begin[p+1]) work on problem p.
 struct MulBatch {
     int n;
+    int delay_ns;  // experiment knob (EFFORT_DELAY_NS): spin this long between the cutoff and the row list
     int cta_begin[kMulBatchMax + 1];
     MulProblem p[kMulBatchMax];
 };
@@ -267,6 +268,58 @@ __device__ __forceinline__ void stream_rows(const uint2* __restrict__ list, int 
     }
 }
 
+// Same walk with the rows staged through a per-warp shared-memory ring filled by cp.async: D row slices
+// (D x 32 lanes x VEC*2 bytes) are ALWAYS in flight per warp at no register cost -- the register-buffered loop
+// above keeps U (8) -- which is what the long-scoreboard stalls of the streaming phase ask for (ncu: 4.7 stalled
+// warps per issue on global loads).  A lane copies and later reads back only its own bytes, so the ring needs no
+// barrier: cp.async.wait_group orders the lane's copies before its loads.
+template <int SLOTS, int VEC, int D>
+__device__ __forceinline__ void stream_rows_ring(const uint2* __restrict__ list, int n_list,
+                                                 const uint16_t* __restrict__ bk, int C, int slice, const MulGeom g,
+                                                 uint32_t tile_saddr, uint32_t ring_saddr, int warp, int n_stream_warps) {
+    static_assert((D & (D - 1)) == 0, "ring depth must be a power of two");
+    constexpr int LB = VEC * 2;       // bytes per lane per row slice
+    constexpr int NWD = (VEC + 1) / 2;
+    const int lane = threadIdx.x & 31;
+    const int rowslot = lane / g.lpr;
+    const int col = slice * 32 * VEC + (lane % g.lpr) * VEC;
+    const bool lane_on = (col < C) && (rowslot < g.R);
+    const uint32_t base_lane = tile_saddr | (uint32_t)(lane * 4);
+    const uint16_t* bk_col = bk + col;
+    const int stride = n_stream_warps * g.R;
+    const int first = warp * g.R + rowslot;
+    const int nsteps = (n_list + stride - 1) / stride;
+    const uint64_t pol = l2_policy_evict_first();
+    const uint32_t my_ring = ring_saddr + (uint32_t)lane * LB;
+    auto issue = [&](int n) {
+        const int e = n * stride + first;
+        if (lane_on && e < n_list) cp_async_hint<LB>(my_ring + (uint32_t)(n & (D - 1)) * (32 * LB), bk_col + (size_t)list[e].y, pol);
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int n = 0; n < D; n++) issue(n);
+#pragma unroll 4
+    for (int n = 0; n < nsteps; n++) {
+        cp_async_wait<D - 1>();
+        const int e = n * stride + first;
+        const bool ok = lane_on && (e < n_list);
+        float val = 0.f;
+        uint32_t w[NWD];
+#pragma unroll
+        for (int j = 0; j < NWD; j++) w[j] = 0u;
+        if (ok) {
+            val = __uint_as_float(list[e].x);
+            const uint32_t a = my_ring + (uint32_t)(n & (D - 1)) * (32 * LB);
+            if constexpr (VEC == 8) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(a));
+            else if constexpr (VEC == 4) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "r"(a));
+            else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[0]) : "r"(a));
+        }
+        accumulate_words<SLOTS, VEC>(base_lane, val, w);
+        issue(n + D);
+    }
+    cp_async_wait<0>();
+}
+
 template <int NW>
 struct MulSmemHeader {
     CutoffSmem cut;
@@ -280,8 +333,10 @@ struct MulSmem {
     static constexpr int kTileFloats = SLOTS * 32 * VEC;
     static constexpr int kTileBytes = kTileFloats * 4;
     static constexpr size_t kHdrBytes = (sizeof(MulSmemHeader<NW>) + 15) & ~size_t(15);
-    static __host__ __device__ size_t bytes(int list_cap) {
-        return (size_t)kTileBytes /*alignment slack*/ + (size_t)NW * kTileBytes + kHdrBytes + (size_t)list_cap * 8;
+    static __host__ __device__ size_t ring_bytes(int ring_depth) { return (size_t)NW * ring_depth * 32 * VEC * 2; }
+    static __host__ __device__ size_t bytes(int list_cap, int ring_depth = 0) {
+        return (size_t)kTileBytes /*alignment slack*/ + (size_t)NW * kTileBytes + kHdrBytes + ring_bytes(ring_depth) +
+               (size_t)list_cap * 8;
     }
 };
 
@@ -290,11 +345,12 @@ struct MulSmemView {
     float* tiles;          // generic pointer to tile 0
     uint32_t tiles_saddr;  // shared-window address of tile 0 (aligned to the tile size)
     MulSmemHeader<NW>* hdr;
+    uint32_t ring_saddr;   // shared-window address of the cp.async ring (warp w: + w * D * 32 * VEC * 2)
     uint2* list;
 };
 
 template <int SLOTS, int VEC, int NW>
-__device__ __forceinline__ MulSmemView<NW> carve_smem(unsigned char* raw) {
+__device__ __forceinline__ MulSmemView<NW> carve_smem(unsigned char* raw, int ring_depth = 0) {
     using L = MulSmem<SLOTS, VEC, NW>;
     const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(raw);
     const uint32_t s1 = (s0 + (uint32_t)L::kTileBytes - 1u) & ~((uint32_t)L::kTileBytes - 1u);
@@ -304,7 +360,8 @@ __device__ __forceinline__ MulSmemView<NW> carve_smem(unsigned char* raw) {
     v.tiles_saddr = s1;
     p += (size_t)NW * L::kTileBytes;
     v.hdr = reinterpret_cast<MulSmemHeader<NW>*>(p);
-    v.list = reinterpret_cast<uint2*>(p + L::kHdrBytes);
+    v.ring_saddr = s1 + (uint32_t)((size_t)NW * L::kTileBytes + L::kHdrBytes);
+    v.list = reinterpret_cast<uint2*>(p + L::kHdrBytes + L::ring_bytes(ring_depth));
     return v;
 }
 
@@ -350,13 +407,13 @@ __device__ __forceinline__ void reduce_tiles_to_partial(const float* __restrict_
 }
 
 // ---- fused kernel: cutoff (optional) + selection + gather-MAC + CTA partial -------------------------
-template <int SLOTS, int VEC, int U, int NW, bool NORM>
+template <int SLOTS, int VEC, int U, int NW, bool NORM, int RING>
 __global__ void __launch_bounds__(NW * 32, 1)
 bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using L = MulSmem<SLOTS, VEC, NW>;
     constexpr int NT = NW * 32;
-    const MulSmemView<NW> sv = carve_smem<SLOTS, VEC, NW>(smem_raw);
+    const MulSmemView<NW> sv = carve_smem<SLOTS, VEC, NW>(smem_raw, RING);
     MulSmemHeader<NW>& hdr = *sv.hdr;
     uint2* list = sv.list;
 
@@ -421,9 +478,16 @@ bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
         }
     }
 
+    // the cutoff is computed by the first kCutWarps warps (cutoff.cuh, group path)
+#ifdef EFFORT_CUT_OLD
     constexpr int PER = (EFFORT_PROBES_MAX + NT - 1) / NT;
     uint16_t prb[PER];
     if (!pb.cutoff_in) load_probes(pb.probes, e_no, pb.n_probes, prb, keep);
+#else
+    const bool cut_thread = !pb.cutoff_in && tid < kCutThreads;
+    GroupProbes prb;
+    if (cut_thread) group_load_probes(pb.probes + (size_t)e_no * pb.n_probes, pb.n_probes, tid, prb, keep);
+#endif
     // everything above read only constant weight metadata: under PDL it overlaps the previous kernel's tail.
     zero_my_tile<SLOTS, VEC, NW>(sv.tiles);  // while those loads are in flight
     EFFORT_TRACE(1);
@@ -446,14 +510,28 @@ bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
     if (pb.cutoff_in) {
         cutoff = *pb.cutoff_in;
     } else {
+#ifdef EFFORT_CUT_OLD
         float vals[PER];
         score_loaded<NORM>(pb.v_cut, prb, pb.n_probes, vals, pb.norm_w, denom);
         EFFORT_TRACE(3);
-        cutoff = block_bisect_cutoff<NW>(vals, pb.n_probes, pb.q, hdr.cut, nullptr,
-                                     pb.trace ? pb.trace + (size_t)blockIdx.x * 16 : nullptr);
+        cutoff = block_bisect_cutoff<NW>(vals, pb.n_probes, pb.q, hdr.cut, nullptr, nullptr);
+#else
+        if (cut_thread) {
+            GroupProducts gp;
+            group_score<NORM>(pb.v_cut, prb, pb.n_probes, tid, gp, pb.norm_w, denom);
+            EFFORT_TRACE(3);
+            group_cutoff<1>(gp, pb.n_probes, pb.q, hdr.cut, tid, pb.trace ? pb.trace + (size_t)blockIdx.x * 16 : nullptr);
+        }
+        __syncthreads();
+        cutoff = hdr.cut.result;
+#endif
     }
     if (pb.cutoff_out && lb == 0 && tid == 0) *pb.cutoff_out = cutoff;
     EFFORT_TRACE(6);
+    if (batch.delay_ns > 0) {
+        const unsigned long long t0 = gtime_ns();
+        while (gtime_ns() - t0 < (unsigned long long)batch.delay_ns) { }
+    }
 
     // 2. selection + compaction.  Thread order == (input, rank) order == ascending row order, so the list
     //    is deterministic and consecutive entries are consecutive rows in HBM.
@@ -541,8 +619,12 @@ bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
     EFFORT_TRACE(8);
 
     // 3. stream the selected rows
-    stream_rows<SLOTS, VEC, U>(list, n_list, pb.bk, pb.C, slice, g,
-                               sv.tiles_saddr + (uint32_t)warp * L::kTileBytes, warp, NW);
+    if constexpr (RING > 0)
+        stream_rows_ring<SLOTS, VEC, RING>(list, n_list, pb.bk, pb.C, slice, g, sv.tiles_saddr + (uint32_t)warp * L::kTileBytes,
+                                           sv.ring_saddr + (uint32_t)warp * (RING * 32 * VEC * 2), warp, NW);
+    else
+        stream_rows<SLOTS, VEC, U>(list, n_list, pb.bk, pb.C, slice, g,
+                                   sv.tiles_saddr + (uint32_t)warp * L::kTileBytes, warp, NW);
     __syncthreads();
     EFFORT_TRACE(9);
 

@@ -1,5 +1,6 @@
 // common.cuh -- shared device helpers for the effort_b200 kernels (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,6 +30,17 @@ __device__ __forceinline__ float half_bits_to_float(uint16_t b) {
 __device__ __forceinline__ bool row_selected(float cutoff, float stat, float v) {
     return cutoff < __fmul_rn(__fmul_rn(kCutoffScale, stat), fabsf(v));
 }
+
+// asynchronous global -> shared copy of BYTES (4, 8 or 16) with an L2 cache-policy hint; completion is tracked by
+// the issuing thread's cp.async groups
+template <int BYTES>
+__device__ __forceinline__ void cp_async_hint(uint32_t dst_saddr, const void* src, uint64_t pol) {
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], %2, %3;" ::"r"(dst_saddr), "l"(src), "n"(BYTES), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // streaming 8/16-byte loads that do not allocate in L1 (weights are read once)
 __device__ __forceinline__ uint2 ldg_stream_u2(const void* p) {

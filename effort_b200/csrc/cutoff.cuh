@@ -34,14 +34,16 @@ struct __align__(16) CutoffSmem {
     float red_min[32];
     float red_max[32];
     float inside[kCutoffInsideMax];
+    float sorted[kCutoffInsideMax];   // group path: the inside products in descending order
     int n_inside;
     float result;
     int loops;
-    // direct method (block_cutoff_direct)
+#ifdef EFFORT_CUTOFF_DIRECT  // direct method (block_cutoff_direct), study only
     unsigned hist[2048];   // products per 16-code bin of the 15-bit bf16 key
     int sub[5][16];        // per target rank: products per code inside its bin
     int wsum[32];
     int tbin[5], trank[5];
+#endif
 };
 
 struct BisectState {
@@ -69,6 +71,22 @@ __device__ __forceinline__ bool bisect_step(BisectState& s, int countAbove, int 
         return true;
     }
     return false;
+}
+
+// The same iteration without early-return branches (one select per state variable, one predicate out).
+__device__ __forceinline__ bool bisect_step_flat(BisectState& s, int countAbove, int effort) {
+    const bool left = countAbove < effort;
+    const float b = s.newBound;
+    s.maxBound = left ? b : s.maxBound;
+    s.maxCount = left ? countAbove : s.maxCount;
+    s.minBound = left ? s.minBound : b;
+    s.minCount = left ? s.minCount : countAbove;
+    s.newBound = (s.maxBound + s.minBound) / 2;
+    const bool e1 = (countAbove == effort) | (s.maxBound - s.minBound < 0.00001f) | (abs(s.maxCount - s.minCount) < 3);
+    const bool e2 = s.loops > 100;
+    const bool e3 = s.newBound == b;  // fixpoint: the reference would idle to loops == 101
+    s.loops = (!e1 & !e2 & e3) ? 101 : s.loops;
+    return e1 | e2 | e3;
 }
 
 // Initial bracket (bucketMul.metal:155-197).  Whole CTA; every thread passes its PER values (< 0 = no value).
@@ -232,6 +250,313 @@ __device__ __forceinline__ float bisect_finish(const float (&vals)[PER], BisectS
     return s.newBound;
 }
 
+// ---- group path (the one the fused kernel and the stand-alone launch use) --------------------------------
+// The block-wide path above is latency-bound on a serial chain of predicated adds and on the work every thread
+// replicates, so the cutoff runs on FOUR warps (the others are free), 32 products per thread:
+//   * the products are bf16 values, so they are kept packed two per register and counted with HSET2.BF16 +
+//     HADD2.BF16: for a bf16 x and an fp32 threshold t >= 0,  x > t  <=>  x > trunc_bf16(t)  -- exact;
+//   * phase A: the same two-iterations-per-round scheme, 128-thread named barrier;
+//   * the <= 128 products left inside the bracket are compacted as keys (value bits | slot: unique, ordered like
+//     the values) and rank-sorted by counting (thread t ranks key t), which yields the five order statistics
+//     T_{k-2..k+2} of the whole product set (ranks above the bracket are +inf, ranks below it can never exceed
+//     a later midpoint);
+//   * ONE thread replays the remaining reference iterations with the capped count
+//         c'(b) = (k-3) + sum_j [T_j > b] = clamp(count(b), k-3, k+2)
+//     (the loop only ever tests count < k, count == k and |maxCount - minCount| < 3; see "direct method" below
+//     and tests/test_oracle.py for the proof).  The bracket update needs only [T_k > b], so the loop-carried
+//     chain is compare -> select -> add -> mul.
+constexpr int kCutWarps = 4;
+constexpr int kCutThreads = kCutWarps * 32;
+constexpr int kCutPer = 32;                          // products per group thread
+constexpr int kCutPairs = kCutPer / 2;
+constexpr int kCutGroupMax = kCutThreads * kCutPer;  // 4096 = probesCount (bucketMul.swift:19)
+
+struct GroupProbes { uint4 w[kCutPer / 8]; };  // fp16 codes; element (c, m) <-> probe (c*128 + gt)*8 + m
+struct GroupProducts {
+    uint32_t pv[kCutPairs];  // bf16x2; 0xBF80 (-1) = no product
+    float tmin, tmax;        // this thread's min / max over its products (:155-163)
+};
+
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+__device__ __forceinline__ unsigned long long cut_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// -1 if a > b else 0 (FSET): lets the five compares of the replay feed a two-level IADD3 tree
+__device__ __forceinline__ int fgt_mask(float a, float b) {
+    int d;
+    asm("set.gt.s32.f32 %0, %1, %2;" : "=r"(d) : "f"(a), "f"(b));
+    return d;
+}
+__device__ __forceinline__ __nv_bfloat162 as_bf162(uint32_t u) { return *reinterpret_cast<__nv_bfloat162*>(&u); }
+__device__ __forceinline__ uint32_t bf162_bits(__nv_bfloat162 h) { return *reinterpret_cast<uint32_t*>(&h); }
+// fp32 threshold (>= 0) -> truncated bf16 in both halves
+__device__ __forceinline__ __nv_bfloat162 thr2(float t) {
+    const uint32_t hi = __float_as_uint(t) & 0xFFFF0000u;
+    return as_bf162(hi | (hi >> 16));
+}
+// sum of the two bf16 halves (small exact integers) as int
+__device__ __forceinline__ int bf162_count(__nv_bfloat162 a) {
+    const uint32_t u = bf162_bits(a);
+    return (int)(__uint_as_float(u << 16) + __uint_as_float(u & 0xFFFF0000u));
+}
+
+// probes already points at the expert's n_probes codes.  Constant data: may be issued before a PDL wait.
+__device__ __forceinline__ void group_load_probes(const __half* __restrict__ probes, int n_probes, int gt,
+                                                  GroupProbes& pr, uint64_t keep) {
+    const bool vec = ((n_probes & 7) == 0) && aligned16(probes);
+#pragma unroll
+    for (int c = 0; c < kCutPer / 8; c++) {
+        const int i0 = (c * kCutThreads + gt) * 8;
+        if (vec && i0 + 8 <= n_probes) {
+            pr.w[c] = ldg_keep_u4(reinterpret_cast<const uint4*>(probes + i0), keep);
+        } else {
+            uint32_t h[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int m = 0; m < 8; m++)
+                if (i0 + m < n_probes) h[m >> 1] |= (uint32_t)ldg_keep_u16(probes + i0 + m, keep) << (16 * (m & 1));
+            pr.w[c] = make_uint4(h[0], h[1], h[2], h[3]);
+        }
+    }
+}
+
+// products of group thread gt: bfloat(|1e5 * v[i] * bfloat(probes[i])|)  (bucketMul.metal:158-163)
+template <bool NORM>
+__device__ __forceinline__ void group_score(const float* __restrict__ v, const GroupProbes& pr, int n_probes, int gt,
+                                            GroupProducts& gp, const __half* __restrict__ norm_w, float denom) {
+    const bool vec = ((n_probes & 7) == 0) && aligned16(v) && (!NORM || aligned16(norm_w));
+    // cvt.rn.bf16x2.f32 is the same round-to-nearest-even as bf16_round (NaN payloads aside: a NaN never counts)
+    __nv_bfloat162 mn2 = as_bf162(0x7F807F80u), mx2 = as_bf162(0xBF80BF80u);  // +inf / -1: neutral for min / max
+#pragma unroll
+    for (int c = 0; c < kCutPer / 8; c++) {
+        const int i0 = (c * kCutThreads + gt) * 8;
+        float vv[8];
+        uint32_t nw[4] = {0u, 0u, 0u, 0u};
+        if (vec && i0 + 8 <= n_probes) {
+            const float4 a = *reinterpret_cast<const float4*>(v + i0), b = *reinterpret_cast<const float4*>(v + i0 + 4);
+            vv[0] = a.x; vv[1] = a.y; vv[2] = a.z; vv[3] = a.w; vv[4] = b.x; vv[5] = b.y; vv[6] = b.z; vv[7] = b.w;
+            if constexpr (NORM) {
+                const uint4 t = *reinterpret_cast<const uint4*>(norm_w + i0);
+                nw[0] = t.x; nw[1] = t.y; nw[2] = t.z; nw[3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                vv[m] = (i0 + m < n_probes) ? v[i0 + m] : 0.f;
+                if constexpr (NORM)
+                    if (i0 + m < n_probes)
+                        nw[m >> 1] |= (uint32_t)__half_as_ushort(norm_w[i0 + m]) << (16 * (m & 1));
+            }
+        }
+        const uint32_t pw[4] = {pr.w[c].x, pr.w[c].y, pr.w[c].z, pr.w[c].w};
+#pragma unroll
+        for (int m2 = 0; m2 < 4; m2++) {
+            const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&pw[m2]));
+            const uint32_t pb = bf162_bits(__floats2bfloat162_rn(pf.x, pf.y));  // bfloat(probe)
+            float v0 = vv[2 * m2], v1 = vv[2 * m2 + 1];
+            if constexpr (NORM) {
+                const float2 wf = __half22float2(*reinterpret_cast<const __half2*>(&nw[m2]));
+                v0 = (v0 / denom) * wf.x;
+                v1 = (v1 / denom) * wf.y;
+            }
+            const float x0 = fabsf(__fmul_rn(__fmul_rn(kCutoffScale, v0), __uint_as_float(pb << 16)));
+            const float x1 = fabsf(__fmul_rn(__fmul_rn(kCutoffScale, v1), __uint_as_float(pb & 0xFFFF0000u)));
+            uint32_t xb = bf162_bits(__floats2bfloat162_rn(x0, x1));
+            if (i0 + 2 * m2 >= n_probes) xb = (xb & 0xFFFF0000u) | 0xBF80u;       // no product: -1
+            if (i0 + 2 * m2 + 1 >= n_probes) xb = (xb & 0x0000FFFFu) | 0xBF800000u;
+            gp.pv[c * 4 + m2] = xb;
+            mx2 = __hmax2(mx2, as_bf162(xb));  // maxNum semantics: NaN is ignored, like the reference's compares
+            uint32_t xm = xb;                  // for the minimum "no product" must be +inf
+            if (i0 + 2 * m2 >= n_probes) xm = (xm & 0xFFFF0000u) | 0x7F80u;
+            if (i0 + 2 * m2 + 1 >= n_probes) xm = (xm & 0x0000FFFFu) | 0x7F800000u;
+            mn2 = __hmin2(mn2, as_bf162(xm));
+        }
+    }
+    const uint32_t mnb = bf162_bits(mn2), mxb = bf162_bits(mx2);
+    gp.tmin = fminf(999.f, fminf(__uint_as_float(mnb << 16), __uint_as_float(mnb & 0xFFFF0000u)));   // :155-163
+    gp.tmax = fmaxf(-999.f, fmaxf(__uint_as_float(mxb << 16), __uint_as_float(mxb & 0xFFFF0000u)));
+}
+
+// Called by the kCutThreads threads of the group (gt = index inside it).  Leaves the cutoff in sm.result and the
+// reference's loop count in sm.loops; the caller publishes them with a barrier that includes the group.
+template <int bar_id>
+__device__ __forceinline__ void group_cutoff(const GroupProducts& gp, int n_probes, int q, CutoffSmem& sm, int gt,
+                                             unsigned long long* trace = nullptr) {
+    const int lane = gt & 31, gwarp = gt >> 5;
+    const int k = n_probes - q;  // bucketMul.metal:154
+    uint32_t* keys = reinterpret_cast<uint32_t*>(sm.inside);
+    uint32_t* sorted = reinterpret_cast<uint32_t*>(sm.sorted);
+    float tmin = gp.tmin, tmax = gp.tmax;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    }
+    if (lane == 0) { sm.red_min[gwarp] = tmin; sm.red_max[gwarp] = tmax; }
+    keys[gt] = 0u;  // padding: below every key that is ranked
+    if (gt == 0) sm.n_inside = 0;
+    group_bar(bar_id, kCutThreads);
+    float gmin = (lane < kCutWarps) ? sm.red_min[lane] : 999.f;
+    float gmax = (lane < kCutWarps) ? sm.red_max[lane] : -999.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
+        gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    }
+    BisectState s;
+    s.minBound = bf16_round(gmin);  // tgMin/tgMax are bfloat (:172-181): the 999 sentinel becomes 1000
+    s.maxBound = bf16_round(gmax);
+    s.newBound = (s.minBound + s.maxBound) / 2;
+    s.loops = 0; s.minCount = 4096; s.maxCount = 0;  // literals of the kernel (:197, :168-169)
+    if (trace && gt == 0) trace[4] = cut_gtime();
+
+    // phase A: two reference iterations per round
+    bool done = false;
+    int buf = 0;
+    while (!done && (s.minCount - s.maxCount) > kCutoffInsideMax) {
+        const float t0 = s.newBound;
+        const float tL = (t0 + s.minBound) / 2;   // next midpoint if count(t0) <  k (maxBound := t0)
+        const float tR = (s.maxBound + t0) / 2;   // next midpoint if count(t0) >= k (minBound := t0)
+        const __nv_bfloat162 b0 = thr2(t0), bL = thr2(tL), bR = thr2(tR);
+        __nv_bfloat162 a0 = as_bf162(0u), aL = as_bf162(0u), aR = as_bf162(0u);
+#pragma unroll
+        for (int j = 0; j < kCutPairs; j++) {
+            const __nv_bfloat162 x = as_bf162(gp.pv[j]);
+            a0 = __hadd2(a0, __hgt2(x, b0));
+            aL = __hadd2(aL, __hgt2(x, bL));
+            aR = __hadd2(aR, __hgt2(x, bR));
+        }
+        int c0 = bf162_count(a0);
+        int cLR = bf162_count(aL) | (bf162_count(aR) << 16);
+        c0 = warp_sum_i(c0);
+        cLR = warp_sum_i(cLR);
+        if (lane == 0) { sm.cnt2[buf][0][gwarp] = c0; sm.cnt2[buf][1][gwarp] = cLR; }
+        group_bar(bar_id, kCutThreads);
+        const int4 ca = *reinterpret_cast<const int4*>(&sm.cnt2[buf][0][0]);
+        const int4 cb = *reinterpret_cast<const int4*>(&sm.cnt2[buf][1][0]);
+        const int n0 = (ca.x + ca.y) + (ca.z + ca.w);
+        const int nLR = (cb.x + cb.y) + (cb.z + cb.w);
+        buf ^= 1;
+        s.loops++;
+        const bool went_left = n0 < k;
+        done = bisect_step_flat(s, n0, k);
+        if (!done && (s.minCount - s.maxCount) > kCutoffInsideMax) {
+            s.loops++;  // s.newBound is now exactly tL or tR (same expression, same operands)
+            done = bisect_step_flat(s, went_left ? (nLR & 0xFFFF) : (nLR >> 16), k);
+        }
+    }
+    if (trace && gt == 0) { trace[5] = cut_gtime(); trace[11] = (unsigned long long)s.loops; }
+    if (!done) {
+        // <= kCutoffInsideMax products are left inside (minBound, maxBound]: compact their keys (one
+        // shared-memory atomic per warp: thread counts, warp scan, warp base)
+        const __nv_bfloat162 bm = thr2(s.minBound), bM = thr2(s.maxBound);
+        uint32_t in_mask[kCutPairs];
+        int mine = 0;
+#pragma unroll
+        for (int j = 0; j < kCutPairs; j++) {
+            const __nv_bfloat162 x = as_bf162(gp.pv[j]);
+            in_mask[j] = __hgt2_mask(x, bm) & ~__hgt2_mask(x, bM);  // x > minBound && !(x > maxBound)
+            mine += (int)(in_mask[j] & 1u) + (int)(in_mask[j] >> 31);
+        }
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int wbase = 0;
+        if (lane == 31 && incl) wbase = atomicAdd(&sm.n_inside, incl);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        {
+            int pos = wbase + incl - mine;
+#pragma unroll
+            for (int j = 0; j < kCutPairs; j++) {  // predicated stores, no branches
+                const int lo = (int)(in_mask[j] & 1u), hi = (int)(in_mask[j] >> 31);
+                if (lo & (pos < kCutoffInsideMax)) keys[pos] = (gp.pv[j] << 16) | (uint32_t)pos;
+                pos += lo;
+                if (hi & (pos < kCutoffInsideMax)) keys[pos] = (gp.pv[j] & 0xFFFF0000u) | (uint32_t)pos;
+                pos += hi;
+            }
+        }
+        group_bar(bar_id, kCutThreads);
+        if (trace && gt == 0) trace[14] = cut_gtime();
+        const int n_in = min(sm.n_inside, kCutoffInsideMax);
+        const uint32_t x = keys[gt];
+        int r0 = 0, r1 = 0, r2 = 0, r3 = 0;  // descending rank of key gt among the n_in keys
+        const int n4 = (n_in + 3) >> 2;
+#pragma unroll 8
+        for (int j4 = 0; j4 < n4; j4++) {
+            const uint4 y = *reinterpret_cast<const uint4*>(&keys[j4 * 4]);
+            r0 += (y.x > x) ? 1 : 0;
+            r1 += (y.y > x) ? 1 : 0;
+            r2 += (y.z > x) ? 1 : 0;
+            r3 += (y.w > x) ? 1 : 0;
+        }
+        if (gt < n_in) sorted[(r0 + r1) + (r2 + r3)] = x;  // padding (0) is never above a key and is not ranked
+        group_bar(bar_id, kCutThreads);
+        if (trace && gt == 0) trace[13] = cut_gtime();
+        if (gt == 0) {
+            const int above = s.maxCount;  // exact number of products > maxBound (0 while maxBound is the maximum)
+            float T[5];
+#pragma unroll
+            for (int ri = 0; ri < 5; ri++) {
+                const int idx = (k - 2 + ri) - above - 1;  // 0-based rank inside the bracket
+                T[ri] = (idx < 0) ? __int_as_float(0x7F800000)
+                                  : (idx >= n_in ? -1.f : __uint_as_float(sorted[idx] & 0xFFFF0000u));
+            }
+            // scalar replay in the capped domain; same statements as bisect_step, arranged so that the
+            // loop-carried chain is  [T_k > b] -> select -> add -> mul
+            float minB = s.minBound, maxB = s.maxBound, nb = s.newBound;
+            int minC = min(s.minCount, k + 2), maxC = max(s.maxCount, k - 3), loops = s.loops, iters = 0;
+            // four iterations per trip: the exit tests (a long predicate chain) of one iteration overlap the
+            // bracket updates of the next ones; the first iteration that exits provides the result
+            struct Rp { float minB, maxB, nb; int minC, maxC; };
+            Rp r = {minB, maxB, nb, minC, maxC};
+            auto step = [&](Rp& q, int loops_now, bool& stop, bool& fix) {
+                const float bnd = q.nb;
+                const bool left = !(T[2] > bnd);  // count(b) < k
+                const int c = (k - 3) - ((fgt_mask(T[0], bnd) + fgt_mask(T[1], bnd) + fgt_mask(T[2], bnd)) +
+                                         (fgt_mask(T[3], bnd) + fgt_mask(T[4], bnd)));
+                q.maxB = left ? bnd : q.maxB;
+                q.minB = left ? q.minB : bnd;
+                q.maxC = left ? c : q.maxC;
+                q.minC = left ? q.minC : c;
+                q.nb = (q.maxB + q.minB) / 2;
+                const bool e1 = (c == k) | (q.maxB - q.minB < 0.00001f) | (abs(q.maxC - q.minC) < 3);
+                const bool e2 = loops_now > 100;
+                const bool e3 = q.nb == bnd;  // fixpoint: the reference would idle to its loop cap
+                fix = !e1 & !e2 & e3;
+                stop = e1 | e2 | e3;
+            };
+            while (true) {
+                bool s1, s2, s3, s4, f1, f2, f3, f4;
+                Rp r1 = r;  step(r1, loops + 1, s1, f1);
+                Rp r2 = r1; step(r2, loops + 2, s2, f2);
+                Rp r3 = r2; step(r3, loops + 3, s3, f3);
+                Rp r4 = r3; step(r4, loops + 4, s4, f4);
+                if (s1 | s2 | s3 | s4) {
+                    const int n = s1 ? 1 : (s2 ? 2 : (s3 ? 3 : 4));
+                    const bool fx = s1 ? f1 : (s2 ? f2 : (s3 ? f3 : f4));
+                    nb = s1 ? r1.nb : (s2 ? r2.nb : (s3 ? r3.nb : r4.nb));
+                    iters += n;
+                    loops = fx ? 101 : loops + n;
+                    break;
+                }
+                r = r4;
+                loops += 4;
+                iters += 4;
+            }
+            sm.result = nb;
+            sm.loops = loops;
+            if (trace) { trace[12] = (unsigned long long)loops; trace[15] = (unsigned long long)iters; }
+        }
+    } else if (gt == 0) {
+        sm.result = s.newBound;
+        sm.loops = s.loops;
+    }
+}
+
 // ---- direct method -----------------------------------------------------------------------------------
 // The bisection never looks at the products themselves, only at count(b) = #{products > b}, and then only
 //   (1) count(b) < k          <=>  b >= T_k                      (T_j = j-th largest product, k = 4096 - q)
@@ -243,6 +568,7 @@ __device__ __forceinline__ float bisect_finish(const float (&vals)[PER], BisectS
 // bf16 codes, then the 16 codes of each target bin) find T_{k-2..k+2} exactly -- ties of any multiplicity
 // included -- and ONE warp replays the reference iterations (same bisect_step, same loop count) with five
 // compares per iteration instead of a block-wide count.  Bit-identical to the iterative path (tests).
+#ifdef EFFORT_CUTOFF_DIRECT
 template <int PER>
 __device__ __forceinline__ float block_cutoff_direct(const float (&vals)[PER], int n_probes, int q, CutoffSmem& sm,
                                                      int* loops_out) {
@@ -371,6 +697,8 @@ __device__ __forceinline__ float block_cutoff_direct(const float (&vals)[PER], i
     return sm.result;
 }
 
+#endif
+
 // Whole-CTA bisection (stand-alone kernel and the non-overlapped fused path).
 template <int NWB, int PER>
 __device__ __forceinline__ float block_bisect_cutoff(const float (&vals)[PER], int n_probes, int q,
@@ -448,6 +776,18 @@ find_cutoff_kernel(const float* __restrict__ v, const __half* __restrict__ probe
                    float* __restrict__ cutoff_out, int* __restrict__ loops_out) {
     __shared__ CutoffSmem sm;
     const uint32_t exp_no = exp_no_dev ? *exp_no_dev : 0u;
+    if (n_probes <= kCutGroupMax) {  // same code path as the fused bucketMul kernel
+        if (threadIdx.x < kCutThreads) {
+            GroupProbes pr;
+            GroupProducts gp;
+            group_load_probes(probes + (size_t)exp_no * n_probes, n_probes, threadIdx.x, pr, l2_policy_evict_last());
+            group_score<false>(v, pr, n_probes, threadIdx.x, gp, nullptr, 1.f);
+            group_cutoff<1>(gp, n_probes, q, sm, threadIdx.x);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { *cutoff_out = sm.result; if (loops_out) *loops_out = sm.loops; }
+        return;
+    }
     float vals[kCutoffMaxPerThread];
     score_probes(v, probes, exp_no, n_probes, vals, l2_policy_evict_last());
     float c = block_bisect_cutoff<kCutoffThreads / 32>(vals, n_probes, q, sm, loops_out);

@@ -284,6 +284,11 @@ static int mul_variant() {
 }
 
 static constexpr size_t kMaxSmem = 227 * 1024;
+static bool ring_enabled() {  // EFFORT_RING=1: cp.async ring instead of the register-buffered streaming loop (measured slower)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EFFORT_RING"); v = (e && atoi(e) == 1) ? 1 : 0; }
+    return v == 1;
+}
 
 static bool overlap_enabled() {
     static int v = -1;
@@ -307,6 +312,7 @@ static int launch_fused_batch(MulCall* calls, int n, int n_cta, cudaStream_t str
     MulBatch batch{};
     IntegrateBatch ib{};
     batch.n = n; ib.n = n;
+    { static int d = -1; if (d < 0) { const char* e = getenv("EFFORT_DELAY_NS"); d = e ? atoi(e) : 0; } batch.delay_ns = d; }
     double total_bytes = 0;
     int cs_sum = 0;
     for (int k = 0; k < n; k++) {
@@ -363,15 +369,32 @@ static int launch_fused_batch(MulCall* calls, int n, int n_cta, cudaStream_t str
         bool norm = batch.p[0].norm_w != nullptr;
         for (int k = 1; k < n; k++)
             if ((batch.p[k].norm_w != nullptr) != norm) return EFFORT_EINVAL;  // a group is all-norm or all-plain
-        if (smem > configured) {
-            CK(cudaFuncSetAttribute(bucket_mul_fused_kernel<SLOTS, VEC, U, NW, false>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaFuncSetAttribute(bucket_mul_fused_kernel<SLOTS, VEC, U, NW, true>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
+        // cp.async ring (16 row slices in flight per warp) when the selection list leaves room for it
+        constexpr int kRing = 16;
+        const size_t smem_ring = MulSmem<SLOTS, VEC, NW>::bytes(list_cap, kRing);
+        const bool ring = ring_enabled() && smem_ring <= kMaxSmem;
+        static size_t configured_ring = 0;
+        if (ring) {
+            if (smem_ring > configured_ring) {
+                CK(cudaFuncSetAttribute(bucket_mul_fused_kernel<SLOTS, VEC, U, NW, false, kRing>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ring));
+                CK(cudaFuncSetAttribute(bucket_mul_fused_kernel<SLOTS, VEC, U, NW, true, kRing>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ring));
+                configured_ring = smem_ring;
+            }
+            if (norm) CK(launch_pdl(bucket_mul_fused_kernel<SLOTS, VEC, U, NW, true, kRing>, dim3(cta), dim3(NW * 32), smem_ring, stream, batch));
+            else CK(launch_pdl(bucket_mul_fused_kernel<SLOTS, VEC, U, NW, false, kRing>, dim3(cta), dim3(NW * 32), smem_ring, stream, batch));
+        } else {
+            if (smem > configured) {
+                CK(cudaFuncSetAttribute(bucket_mul_fused_kernel<SLOTS, VEC, U, NW, false, 0>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CK(cudaFuncSetAttribute(bucket_mul_fused_kernel<SLOTS, VEC, U, NW, true, 0>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured = smem;
+            }
+            if (norm) CK(launch_pdl(bucket_mul_fused_kernel<SLOTS, VEC, U, NW, true, 0>, dim3(cta), dim3(NW * 32), smem, stream, batch));
+            else CK(launch_pdl(bucket_mul_fused_kernel<SLOTS, VEC, U, NW, false, 0>, dim3(cta), dim3(NW * 32), smem, stream, batch));
         }
-        if (norm) CK(launch_pdl(bucket_mul_fused_kernel<SLOTS, VEC, U, NW, true>, dim3(cta), dim3(NW * 32), smem, stream, batch));
-        else CK(launch_pdl(bucket_mul_fused_kernel<SLOTS, VEC, U, NW, false>, dim3(cta), dim3(NW * 32), smem, stream, batch));
     }
     LAUNCHED();
     CK(launch_pdl(integrate_kernel<SLOTS, VEC>, dim3((max_words + 31) / 32, n), dim3(256), 0, stream, ib));

@@ -6,7 +6,10 @@ sys.path.insert(0, ROOT)
 from effort_b200 import ops  # noqa: E402
 from tools.sweep import rand_weights, make_v_gpu  # noqa: E402
 
-for sh, eff in [("4096x1024", 0.25), ("4096x4096", 0.25), ("4096x14336", 0.25), ("4096x14336", 1.0)]:
+CASES = [("4096x1024", 0.25), ("4096x4096", 0.25), ("4096x14336", 0.25), ("4096x14336", 1.0)]
+if os.environ.get("AB_CASES"):   # e.g. AB_CASES=4096x14336:1.0,4096x14336:0.25
+    CASES = [(c.split(":")[0], float(c.split(":")[1])) for c in os.environ["AB_CASES"].split(",")]
+for sh, eff in CASES:
     in_dim, out_dim = (int(x) for x in sh.split("x"))
     ws = [rand_weights(out_dim, in_dim, 100 + c)[0] for c in range(max(3, 400_000_000 // (2 * in_dim * out_dim)))]
     v = make_v_gpu(in_dim)

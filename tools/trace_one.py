@@ -34,10 +34,15 @@ for rep in range(3):
     n = L.effort_debug_read_trace(ctx._h, buf.ctypes.data, 148)
     t = buf[:n, :11].astype(np.int64)
     loops = buf[:n, 11:13]
+    sorted_t = buf[:n, 13].astype(np.int64)
+    comp_t = buf[:n, 14].astype(np.int64)
+    print("   replay iterations:", int(buf[0, 15]), " compacted at median",
+          float(np.median((comp_t[comp_t > 0] - buf[:n, 0].astype(np.int64)[buf[:n, 0] > 0].min()) / 1000.0)) if (comp_t > 0).any() else None)
     t = t[t[:, 0] > 0]
     t0 = t[:, 0].min()
     rel = (t - t0) / 1000.0
     print(f"{a.shape} effort {a.effort} rep {rep}: event total {s.elapsed_time(e)*1000:.1f} us; ctas {len(t)}")
-    print("   loops after phase A / total:", int(loops[0, 0]), int(loops[0, 1]))
+    print("   loops after phase A / total:", int(loops[0, 0]), int(loops[0, 1]),
+          " rank-sorted at median", float(np.median((sorted_t[sorted_t > 0] - t0) / 1000.0)) if (sorted_t > 0).any() else None)
     for k, nm in enumerate(names):
         print(f"   {nm:9s} min {rel[:,k].min():7.2f}  median {np.median(rel[:,k]):7.2f}  max {rel[:,k].max():7.2f} us")
