@@ -122,8 +122,9 @@ def workload_config(args, world):
             "effort": args.effort, "context": f"positions {args.warmup}..{args.warmup + args.steps}",
             "parallelism": "single GPU" if world == 1 else (
                 f"{world} independent replicas" if getattr(args, "replicas", False) else
-                f"tp{world}: q/k/v/w1/w3 column-sharded, wo/w2 row-sharded, NCCL all-gather(cutoff input)+all-reduce per "
-                f"row-parallel GEMV, vocab-sharded lm_head"),
+                f"tp{world}: q/k/v/w1/w3 column-sharded, wo/w2 row-sharded; per row-parallel GEMV one all-gather (cutoff "
+                f"input) + one all-reduce as one-shot NVLink peer-memory kernels fused with silu*mul / residual+rmsNorm "
+                f"(EFFORT_P2P=0: NCCL), vocab-sharded lm_head"),
             "l2": "14 GB of distinct weights per token >> 126 MB L2: no flush needed"}
 
 

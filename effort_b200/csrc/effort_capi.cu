@@ -919,7 +919,8 @@ struct effort_model {
     const __half *norm = nullptr, *out_core = nullptr, *emb = nullptr;
     float *attn_full = nullptr, *x2_full = nullptr, *logits_local = nullptr;  // tensor-parallel gather buffers
     float *sumsq_a = nullptr, *sumsq_b = nullptr;  // per-block sum(h^2) partials for the fused rmsNorm-on-load
-    bool fuse_glue = true;
+    bool fuse_glue = false;  // rmsNorm-on-load / residual+silu in the integrate epilogue: 9 launches per layer, but measured
+                             // slower than the 12-launch chain since the cutoff moved to four warps (the norm divides sit on them)
     float *h = nullptr, *h_norm = nullptr, *xq = nullptr, *xk = nullptr, *xv = nullptr, *attn = nullptr,
           *attn_ffn_out = nullptr, *fxn = nullptr, *x1 = nullptr, *x3 = nullptr, *x2 = nullptr, *ffn_out = nullptr,
           *out_normed = nullptr, *logits = nullptr;
@@ -976,7 +977,7 @@ extern "C" int effort_model_create(effort_ctx_t* ctx, const effort_model_config_
         (rc = model_alloc(m, m->logits_local, cfg->vocab)) || (rc = model_alloc(m, m->sumsq_a, 1024)) ||
         (rc = model_alloc(m, m->sumsq_b, 1024)))
         return rc;
-    { const char* e = getenv("EFFORT_FUSE_GLUE"); m->fuse_glue = !(e && atoi(e) == 0); }
+    { const char* e = getenv("EFFORT_FUSE_GLUE"); m->fuse_glue = e && atoi(e) == 1; }
     CK(cudaMallocHost(&m->h_token, sizeof(int)));
     CK(cudaMallocHost(&m->h_next, sizeof(int)));
     CK(cudaMallocHost(&m->h_logits, sizeof(float) * cfg->vocab));

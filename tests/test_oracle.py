@@ -349,3 +349,75 @@ def test_direct_order_statistic_replay_equals_literal_bisection(conv4096):
                 c, loops = O.find_cutoff(v, r["probes"], e, return_loops=True)
                 c2, loops2 = _direct_cutoff(vals, 4096 - O.effort_to_q(e))
                 assert np.float32(c).view(np.uint32) == np.float32(c2).view(np.uint32) and loops == loops2, (e, c, c2)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the path the CUDA kernels actually run (csrc/cutoff.cuh, group_cutoff): literal iterations while more than 128
+# products lie inside the bracket (counted against bf16-TRUNCATED thresholds, two products per register), then
+# the five order statistics are read from the rank-sorted bracket and one thread replays the rest of the loop in
+# the capped domain, continuing from the state phase A left
+# ---------------------------------------------------------------------------------------------------------
+def _trunc_bf16(t):
+    return (np.float32(t).view(np.uint32) & np.uint32(0xFFFF0000)).view(np.float32)
+
+
+def _group_cutoff(vals, k, inside_max=128):
+    f32 = np.float32
+    bf = lambda x: f32(O.lib().oracle_bf16_round(float(x)))
+    good = vals[vals >= 0]
+    mn = bf(min(f32(999), good.min())) if len(good) else bf(f32(999))
+    mx = bf(max(f32(-999), good.max())) if len(good) else bf(f32(-999))
+    nb, loops, min_c, max_c = f32((mn + mx) / f32(2)), 0, 4096, 0
+
+    def step(c):
+        nonlocal mn, mx, nb, loops, min_c, max_c
+        if c < k:
+            mx, max_c = nb, c
+        else:
+            mn, min_c = nb, c
+        prev, nb = nb, f32((mx + mn) / f32(2))
+        if c == k or f32(mx - mn) < f32(0.00001) or abs(max_c - min_c) < 3 or loops > 100:
+            return True
+        if nb == prev:
+            loops = 101
+            return True
+        return False
+
+    while (min_c - max_c) > inside_max:          # phase A
+        loops += 1
+        c_exact = int(np.count_nonzero(vals > nb))
+        c = int(np.count_nonzero(vals > _trunc_bf16(nb)))   # what HSET2.BF16 computes
+        assert c == c_exact
+        if step(c):
+            return nb, loops
+    inside = np.sort(vals[(vals > mn) & (vals <= mx)])[::-1]
+    assert len(inside) <= inside_max
+    above = max_c
+    assert above == int(np.count_nonzero(vals > mx))
+    T = []
+    for r in range(k - 2, k + 3):
+        idx = r - above - 1
+        T.append(f32(np.inf) if idx < 0 else (f32(-1) if idx >= len(inside) else inside[idx]))
+    min_c, max_c = min(min_c, k + 2), max(max_c, k - 3)
+    while True:                                   # scalar replay
+        loops += 1
+        assert (not (T[2] > nb)) == ((k - 3) + sum(1 for t in T if t > nb) < k)   # the one compare on the critical path
+        if step((k - 3) + sum(1 for t in T if t > nb)):
+            return nb, loops
+
+
+def test_group_cutoff_path_equals_literal_bisection(conv4096):
+    w, r = conv4096
+    rng = np.random.default_rng(1)
+    cases = [make_v(4096, s) for s in range(6)] + [
+        np.zeros(4096, np.float32), np.ones(4096, np.float32), make_v(4096, 3) * 1e4, make_v(4096, 4) * 1e-6,
+        np.eye(1, 4096, 17, dtype=np.float32)[0] * 5, np.round(make_v(4096, 9)), rng.integers(0, 3, 4096).astype(np.float32),
+        np.where(rng.random(4096) < 0.9, 0, make_v(4096, 11)).astype(np.float32)]
+    with np.errstate(all="ignore"):
+        for v in cases:
+            vals = O.probe_vals(v, r["probes"])
+            for e in (1.0, 0.999, 0.9, 0.5, 0.25, 0.1, 0.001, 0.0):
+                c, loops = O.find_cutoff(v, r["probes"], e, return_loops=True)
+                for inside_max in (128, 16):
+                    c2, loops2 = _group_cutoff(vals, 4096 - O.effort_to_q(e), inside_max)
+                    assert np.float32(c).view(np.uint32) == np.float32(c2).view(np.uint32) and loops == loops2, (e, c, c2, loops, loops2)
