@@ -61,7 +61,19 @@ SIGNATURES = {
     "effort_model_set_fused_glue": (C.c_int, [vp, C.c_int]),
     "effort_launch_count": (C.c_uint64, []),
     "effort_last_selected": (C.c_int, [vp, C.POINTER(C.c_uint32), vp]),
+    "effort_loader_open": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "effort_loader_close": (None, [vp]),
+    "effort_loader_count": (C.c_int, [vp]),
+    "effort_loader_name": (C.c_char_p, [vp, C.c_int]),
+    "effort_loader_has": (C.c_int, [vp, C.c_char_p]),
+    "effort_loader_tensor": (C.c_int, [vp, C.c_char_p, vp]),
+    "effort_bf16_to_f16": (C.c_int, [vp, vp, C.c_size_t]),
 }
+
+
+class TensorInfo(C.Structure):
+    _fields_ = [("dtype", C.c_int), ("ndim", C.c_int), ("shape", C.c_int64 * 8), ("data", C.c_void_p),
+                ("nbytes", C.c_size_t)]
 
 
 class ModelConfig(C.Structure):

@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libeffort_b200.so")
-SOURCES = ["effort_capi.cu"]
+SOURCES = ["effort_capi.cu", "safetensors_io.cpp"]
 HEADERS = ["common.cuh", "cutoff.cuh", "bucket_mul.cuh", "convert.cuh", "q4.cuh", "decode.cuh", "comm.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -75,3 +75,78 @@ class TensorLoader:
             raise ValueError(f"{prefix}: shapes {b.shape} / {s.shape} do not match in={in_dim} out={out_dim}")
         return {"buckets": np.ascontiguousarray(b[:rows]), "bucket.stats": np.ascontiguousarray(s[:rows]),
                 "probes": self[prefix + "probes"], "percentLoad": percent_load}
+
+
+class NativeTensorLoader:
+    """The same interface over the library's own reader (csrc/safetensors_io.cpp: `effort_loader_*`, plain C ABI, no
+    Python safetensors package): index json + per-file headers parsed in C++, files mmapped read-only.  Arrays are
+    copies by default; `copy=False` returns read-only views into the mapping that are valid until `close()`."""
+
+    _DT = {0: np.float16, 1: np.uint16, 2: np.float32}  # EFFORT_ST_F16 / BF16 (raw codes) / F32
+
+    def __init__(self, path: str, model: str = MODEL_FP16):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib = C, _lib
+        self._L = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._L.effort_loader_open(path.encode(), model.encode(), C.byref(h)), f"effort_loader_open({path}, {model})")
+        self._h = h
+
+    def close(self):
+        if self._h:
+            self._L.effort_loader_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def names(self):
+        return [self._L.effort_loader_name(self._h, i).decode() for i in range(self._L.effort_loader_count(self._h))]
+
+    def has_tensor(self, name: str) -> bool:
+        return bool(self._L.effort_loader_has(self._h, name.encode()))
+
+    def info(self, name: str):
+        ti = self._lib.TensorInfo()
+        rc = self._L.effort_loader_tensor(self._h, name.encode(), self._C.byref(ti))
+        if rc == -6:  # EFFORT_ENOTLOADED: "not found in the safetensors lib" (safetensors.swift:148)
+            raise KeyError(f"Tensor not found in library: {name}")
+        self._lib.check(rc, f"effort_loader_tensor({name})")
+        return ti
+
+    def get(self, name: str, copy: bool = True, rows: int = None) -> np.ndarray:
+        """rows: keep only the first `rows` entries of the leading dimension (the percentLoad prefix) -- only those
+        bytes are touched."""
+        ti = self.info(name)
+        shape = [int(ti.shape[d]) for d in range(ti.ndim)]
+        nbytes = int(ti.nbytes)
+        if rows is not None and shape:
+            rows = min(rows, shape[0])
+            nbytes = nbytes // max(1, shape[0]) * rows
+            shape[0] = rows
+        buf = (self._C.c_char * nbytes).from_address(ti.data) if nbytes else b""
+        a = np.frombuffer(buf, dtype=self._DT[ti.dtype]).reshape(shape)
+        if ti.dtype == 1:  # BF16 -> fp16 like the reference does after loading (safetensors.swift:207-210)
+            out = np.empty(a.shape, np.float16)
+            self._lib.check(self._L.effort_bf16_to_f16(a.ctypes.data, out.ctypes.data, a.size), "effort_bf16_to_f16")
+            return out
+        if copy:
+            return a.copy()
+        a.flags.writeable = False
+        return a
+
+    __getitem__ = get
+
+    def expert_weights(self, prefix: str, in_dim: int, out_dim: int, percent_load: int = 16) -> dict:
+        """ExpertWeights(prefix...) truncated to the first percent_load ranks (loader.swift:113-166); only the kept
+        prefix of the mapping is read."""
+        rows = percent_load * in_dim
+        bi, si = self.info(prefix + "buckets"), self.info(prefix + "bucket.stats")
+        if (bi.ndim != 2 or (bi.shape[0], bi.shape[1]) != (16 * in_dim, out_dim // 16)) or si.shape[0] != 16 * in_dim:
+            raise ValueError(f"{prefix}: shapes do not match in={in_dim} out={out_dim}")
+        return {"buckets": self.get(prefix + "buckets", rows=rows), "bucket.stats": self.get(prefix + "bucket.stats", rows=rows),
+                "probes": self.get(prefix + "probes"), "percentLoad": percent_load}

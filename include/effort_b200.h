@@ -243,6 +243,35 @@ uint64_t effort_launch_count(void);
 /* rows selected by the last fused bucket_mul on this ctx (synchronises `stream`) */
 int effort_last_selected(effort_ctx_t* ctx, uint32_t* n_selected, void* stream);
 
+/* ---- bucketed-safetensors model directory (host side, no CUDA) --------------------------------------------
+ * Replaces TensorLoader (helpers/safetensors.swift:87-216): `<model>.safetensors.index.json` maps tensor names to
+ * the per-layer files written by TensorSaver.save (:38-85); a name missing from the index is retried as
+ * name + ".weight" (:141-146); only BF16 / F16 / F32 tensors are accepted (:176); data_offsets must span
+ * prod(shape) * sizeof(dtype) bytes (:182).  Files are mapped read-only and stay mapped until effort_loader_close,
+ * so `data` can be passed to cudaMemcpy (or wrapped without a copy).  ExpertWeights (loader.swift:113-166) keeps
+ * only the first percentLoad * inDim rows of `buckets` / `bucket.stats`: rows are the leading dimension, so that
+ * truncation is a prefix of `data` (see effort_b200/weights_io.py, NativeTensorLoader.expert_weights). */
+#define EFFORT_ST_F16 0
+#define EFFORT_ST_BF16 1
+#define EFFORT_ST_F32 2
+#define EFFORT_ST_MAX_DIMS 8
+typedef struct effort_loader effort_loader_t;
+typedef struct {
+    int dtype;                         /* EFFORT_ST_* */
+    int ndim;
+    int64_t shape[EFFORT_ST_MAX_DIMS];
+    const void* data;                  /* inside the read-only mapping */
+    size_t nbytes;
+} effort_tensor_info_t;
+int effort_loader_open(const char* dir, const char* model, effort_loader_t** out);   /* TensorLoader(path:model:) :105-110 */
+void effort_loader_close(effort_loader_t* loader);
+int effort_loader_count(const effort_loader_t* loader);
+const char* effort_loader_name(const effort_loader_t* loader, int i);                /* index order */
+int effort_loader_has(const effort_loader_t* loader, const char* name);              /* hasTensor :132-134 */
+int effort_loader_tensor(effort_loader_t* loader, const char* name, effort_tensor_info_t* info);  /* fetchTensor :136-216 */
+/* convertBF16 (the reference converts BF16 tensors to fp16 after loading, safetensors.swift:207-210) */
+int effort_bf16_to_f16(const uint16_t* src, uint16_t* dst, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

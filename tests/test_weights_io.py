@@ -39,3 +39,110 @@ def test_roundtrip_names_index_and_percent_load(tmp_path):
         L["layers.7.ffn_norm"]
     with pytest.raises(ValueError):
         L.expert_weights("layers.0.attention.wk.", 4096, 4096)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the library's own reader (csrc/safetensors_io.cpp, C ABI effort_loader_*): same files, same answers as the
+# Python safetensors package; TensorLoader's behaviours (helpers/safetensors.swift:136-216) as return codes
+# ---------------------------------------------------------------------------------------------------------
+def _write_model(tmp_path):
+    rng = np.random.default_rng(3)
+    conv = O.bucketize(make_w(1024, 4096, 5))
+    files = []
+    for layer in range(3):
+        t = {f"layers.{layer}.attention_norm": rng.standard_normal(4096).astype(np.float16),
+             f"layers.{layer}.attention.wk.buckets": np.ascontiguousarray(conv["buckets"]),
+             f"layers.{layer}.attention.wk.bucket.stats": np.ascontiguousarray(conv["bucket.stats"]),
+             f"layers.{layer}.attention.wk.probes": np.ascontiguousarray(conv["probes"]),
+             f"layers.{layer}.q4.stats": rng.standard_normal((64, 2)).astype(np.float32)}
+        if layer == 0:
+            t["tok_embeddings.core.weight"] = rng.standard_normal((32, 16)).astype(np.float16)  # reached as "...core"
+        files.append(t)
+    W.save_model(str(tmp_path), files, description='quotes " and \\ and unicode é中 survive')
+    return files
+
+
+def test_native_loader_matches_python_reader(tmp_path):
+    files = _write_model(tmp_path)
+    N, P = W.NativeTensorLoader(str(tmp_path)), W.TensorLoader(str(tmp_path))
+    assert sorted(N.names()) == sorted(k for f in files for k in f)
+    for f in files:
+        for name, want in f.items():
+            got = N[name]
+            assert got.dtype == want.dtype and got.shape == want.shape
+            assert np.array_equal(got.view(np.uint8), np.ascontiguousarray(want).view(np.uint8))
+            assert np.array_equal(P[name].view(np.uint8), got.view(np.uint8))
+    v = N.get("layers.2.attention_norm", copy=False)           # zero-copy view into the mapping
+    assert not v.flags.writeable and np.array_equal(v, files[2]["layers.2.attention_norm"])
+    # fetchTensor's ".weight" fallback (safetensors.swift:141-146)
+    assert N.has_tensor("tok_embeddings.core") and N["tok_embeddings.core"].shape == (32, 16)
+    assert not N.has_tensor("layers.9.attention_norm")
+    with pytest.raises(KeyError):
+        N["layers.9.attention_norm"]
+    # ExpertWeights percentLoad prefix (loader.swift:113-166) == the Python reader's
+    a = N.expert_weights("layers.1.attention.wk.", 4096, 1024, percent_load=5)
+    b = P.expert_weights("layers.1.attention.wk.", 4096, 1024, percent_load=5)
+    for k in ("buckets", "bucket.stats", "probes"):
+        assert a[k].shape == b[k].shape and np.array_equal(a[k].view(np.uint16), b[k].view(np.uint16))
+    with pytest.raises(ValueError):
+        N.expert_weights("layers.1.attention.wk.", 4096, 4096)
+    N.close()
+
+
+def test_native_loader_rejects_bad_containers(tmp_path):
+    from effort_b200._lib import EffortError
+    with pytest.raises(EffortError):                          # no index json
+        W.NativeTensorLoader(str(tmp_path))
+    _write_model(tmp_path)
+    idx = tmp_path / "buckets-FP16.safetensors.index.json"
+    wm = json.load(open(idx))
+    # a tensor of an unsupported dtype is refused when asked for (safetensors.swift:176), the rest still loads
+    from safetensors.numpy import save_file
+    save_file({"ints": np.arange(4, dtype=np.int32), "ok": np.ones(3, np.float32)}, str(tmp_path / "extra.safetensors"))
+    wm["weight_map"].update({"ints": "extra.safetensors", "ok": "extra.safetensors", "ghost": "missing.safetensors",
+                             "trunc": "trunc.safetensors"})
+    json.dump(wm, open(idx, "w"))
+    raw = open(tmp_path / "extra.safetensors", "rb").read()
+    open(tmp_path / "trunc.safetensors", "wb").write(raw[: len(raw) - 7])   # data section shorter than data_offsets say
+    N = W.NativeTensorLoader(str(tmp_path))
+    assert np.array_equal(N["ok"], np.ones(3, np.float32))
+    for bad in ("ints", "ghost", "trunc"):
+        with pytest.raises((EffortError, KeyError)):
+            N[bad]
+    json.dump({"weight_map": ["not", "a", "map"]}, open(idx, "w"))
+    with pytest.raises(EffortError):
+        W.NativeTensorLoader(str(tmp_path))
+    open(idx, "w").write('{"weight_map": {"a": "b"')            # truncated json
+    with pytest.raises(EffortError):
+        W.NativeTensorLoader(str(tmp_path))
+
+
+def test_bf16_tensors_come_back_as_fp16(tmp_path):
+    """convertBF16 (safetensors.swift:207-210): BF16 on disk -> fp16 in memory, value for value."""
+    import struct
+    vals = np.array([0.0, -0.0, 1.0, -2.5, 3.140625, 65280.0, 1e-5, 6.1e-5, 7e4, -1e38, np.inf, -np.inf, 2.0 ** -24, 2.0 ** -26],
+                    np.float32)
+    bf = (vals.view(np.uint32) >> 16).astype(np.uint16)         # exact for these (chosen representable or truncated)
+    vals_bf = (bf.astype(np.uint32) << 16).view(np.float32)
+    hdr = json.dumps({"x": {"dtype": "BF16", "shape": [len(bf)], "data_offsets": [0, 2 * len(bf)]}}).encode()
+    open(tmp_path / "m.safetensors", "wb").write(struct.pack("<Q", len(hdr)) + hdr + bf.tobytes())
+    json.dump({"weight_map": {"x": "m.safetensors"}}, open(tmp_path / "m.safetensors.index.json", "w"))
+    got = W.NativeTensorLoader(str(tmp_path), model="m")["x"]
+    with np.errstate(over="ignore"):
+        want = vals_bf.astype(np.float16)                       # numpy: round-to-nearest-even, overflow -> inf
+    assert got.dtype == np.float16 and np.array_equal(got.view(np.uint16), want.view(np.uint16))
+
+
+def test_bf16_to_f16_all_codes():
+    import ctypes as C
+    from effort_b200 import _lib
+    L = _lib.load()
+    src = np.arange(65536, dtype=np.uint16)
+    dst = np.empty(65536, np.uint16)
+    assert L.effort_bf16_to_f16(src.ctypes.data, dst.ctypes.data, src.size) == 0
+    f32 = (src.astype(np.uint32) << 16).view(np.float32)
+    with np.errstate(over="ignore", invalid="ignore"):
+        want = f32.astype(np.float16).view(np.uint16)
+    nan = np.isnan(f32)
+    assert np.array_equal(dst[~nan], want[~nan])
+    assert np.all(np.isnan(dst[nan].view(np.float16)))
