@@ -138,6 +138,70 @@ class DecodeModel:
         torch.cuda.empty_cache()
         return m
 
+    # -- model directory (the reference's on-disk contract, weights_io.py) ------------------------------------
+    @staticmethod
+    def convert_random_to_directory(path: str, cfg: MistralConfig = MistralConfig(), seed: int = 1234,
+                                    norm_jitter: float = 0.1) -> str:
+        """convertMistral (convert.swift:59-127) on random-init weights: bucketize every projection on the GPU and
+        write one bucketed-safetensors file per layer + the index.  Draws the SAME random sequence as random_init
+        (same seed => same model), so a loaded model can be compared with the in-memory one bit for bit."""
+        from . import weights_io
+        gen = torch.Generator(device="cuda").manual_seed(seed)
+        kvd = cfg.n_kv_heads * cfg.head_dim
+        files = []
+
+        def norm_vec():
+            return (1.0 + norm_jitter * torch.randn(cfg.dim, generator=gen, device="cuda")).half()
+
+        for i in range(cfg.n_layers):
+            names = weights_io.layer_tensor_names(i)
+            t = {}
+            for key, (o, n) in (("wq", (cfg.dim, cfg.dim)), ("wk", (kvd, cfg.dim)), ("wv", (kvd, cfg.dim)), ("wo", (cfg.dim, cfg.dim)),
+                                ("w1", (cfg.hidden_dim, cfg.dim)), ("w2", (cfg.dim, cfg.hidden_dim)), ("w3", (cfg.hidden_dim, cfg.dim))):
+                conv = ops.bucketize(_rand_w(o, n, gen))
+                torch.cuda.synchronize()
+                for part in ("buckets", "bucket.stats", "probes"):
+                    t[names[key] + part] = conv[part].cpu().numpy()
+            t[f"layers.{i}.attention_norm"] = norm_vec().cpu().numpy()
+            t[f"layers.{i}.ffn_norm"] = norm_vec().cpu().numpy()
+            files.append(t)
+        out_core = _rand_w(cfg.vocab, cfg.dim, gen)
+        files[0]["model.norm"] = norm_vec().cpu().numpy()                      # convert.swift:70-74: with layer 0
+        files[0]["output.core"] = out_core.cpu().numpy()
+        files[0]["tok_embeddings.core"] = _rand_w(cfg.vocab, cfg.dim, gen, scale=1.0).cpu().numpy()
+        return weights_io.save_model(path, files)
+
+    @classmethod
+    def from_directory(cls, path: str, cfg: MistralConfig = MistralConfig(), percent_load: int = 16, native: bool = True,
+                       model: str = "buckets-FP16", ctx: Optional[ops.Context] = None) -> "DecodeModel":
+        """Model.init(from: TensorLoader) (model.swift:40-112) over a bucketed-safetensors directory.  native=True
+        reads through the library's C-ABI loader (effort_loader_*), else through the Python safetensors package."""
+        from . import weights_io
+        tl = (weights_io.NativeTensorLoader if native else weights_io.TensorLoader)(path, model)
+        m = cls(cfg, ctx)
+        kvd = cfg.n_kv_heads * cfg.head_dim
+        dims = {"wq": (cfg.dim, cfg.dim), "wk": (cfg.dim, kvd), "wv": (cfg.dim, kvd), "wo": (cfg.dim, cfg.dim),
+                "w1": (cfg.dim, cfg.hidden_dim), "w2": (cfg.hidden_dim, cfg.dim), "w3": (cfg.dim, cfg.hidden_dim)}  # (in, out)
+
+        def dev(a):
+            return torch.from_numpy(a).cuda()
+
+        for i in range(cfg.n_layers):
+            names = weights_io.layer_tensor_names(i)
+            ews = []
+            for key in ("wq", "wk", "wv", "wo", "w1", "w2", "w3"):
+                in_dim, out_dim = dims[key]
+                t = tl.expert_weights(names[key], in_dim, out_dim, percent_load)
+                ew = ops.ExpertWeights(dev(t["buckets"]), dev(t["bucket.stats"]), dev(t["probes"]), inDim=in_dim, outDim=out_dim,
+                                       percentLoad=percent_load)
+                ew.release_reference_layout()
+                ews.append(ew)
+            m.set_layer(i, *ews, dev(tl[f"layers.{i}.attention_norm"]), dev(tl[f"layers.{i}.ffn_norm"]))
+        m.set_head(dev(tl["model.norm"]), dev(tl["output.core"]), dev(tl["tok_embeddings.core"]))
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        return m
+
     # -- run ----------------------------------------------------------------------------------------------
     def reset(self):
         check(self._L.effort_model_reset(self._h, ops._stream_ptr()), "effort_model_reset")

@@ -72,3 +72,36 @@ def test_step_host_and_self_feeding(small_model):
         t = m.step_host(None, effort=0.25)
         seq_b.append(t)
     assert seq_a == seq_b                                  # deterministic generation (the reference's is not)
+
+
+def test_model_directory_roundtrip(tmp_path):
+    """convert -> bucketed-safetensors directory -> load (C-ABI loader and Python reader) -> decode: the loaded models
+    reproduce the in-memory model of the same seed bit for bit (same weights, deterministic kernels); a
+    percentLoad-truncated load (loader.swift:113-166) runs and correlates."""
+    import torch
+    from effort_b200.model import DecodeModel, MistralConfig
+    cfg = MistralConfig(n_layers=1, vocab=1024, max_seq=32)
+    index = DecodeModel.convert_random_to_directory(str(tmp_path), cfg, seed=11)
+    assert index.endswith("buckets-FP16.safetensors.index.json")
+    mem = DecodeModel.random_init(cfg, seed=11)
+    models = {"native": DecodeModel.from_directory(str(tmp_path), cfg, native=True),
+              "python": DecodeModel.from_directory(str(tmp_path), cfg, native=False),
+              "load8": DecodeModel.from_directory(str(tmp_path), cfg, percent_load=8)}
+    outs = {}
+    for name, m in [("mem", mem)] + list(models.items()):
+        m.set_graphs(False)
+        m.reset()
+        seq = []
+        for t in (3, 500, 77):
+            m.step(torch.tensor([t], dtype=torch.int32, device="cuda"), effort=0.25)
+            torch.cuda.synchronize()
+            seq.append(m.logits().cpu().numpy())
+        outs[name] = seq
+    for name in ("native", "python"):
+        for a, b in zip(outs["mem"], outs[name]):
+            assert np.array_equal(a, b), name
+    # percentLoad 8 drops ranks 8..15.  On iid-Gaussian weights those ranks ARE selected at effort 0.25 (the row means
+    # fall slowly with rank), so the truncated model only correlates with the full one (measured 0.86 on the first
+    # token); real Mistral weights are what the reference's percentLoad knob is for (loader.swift:113-166).
+    assert all(np.isfinite(x).all() for x in outs["load8"])
+    assert O.cossim(outs["mem"][0], outs["load8"][0]) > 0.7
