@@ -421,3 +421,22 @@ def test_group_cutoff_path_equals_literal_bisection(conv4096):
                 for inside_max in (128, 16):
                     c2, loops2 = _group_cutoff(vals, 4096 - O.effort_to_q(e), inside_max)
                     assert np.float32(c).view(np.uint32) == np.float32(c2).view(np.uint32) and loops == loops2, (e, c, c2, loops, loops2)
+
+
+def test_multithreaded_cpu_arm_equals_the_single_thread_oracle():
+    """bench.py's CPU arm (oracle_bucket_mul_mt: parallel dispatch, row-chunked MAC into private accumulators) selects
+    the same rows and sums to the same vector as the literal single-thread restatement, for any thread count."""
+    for (i, o) in [(4096, 1024), (4096, 4096)]:
+        r = O.bucketize(make_w(o, i, 5))
+        v = make_v(i, 42)
+        for eff in (0.25, 1.0):
+            ref = O.bucket_mul(v, r["buckets"], r["bucket.stats"], r["probes"], i, o, eff)
+            before = O.num_threads()
+            try:
+                for nt in (1, 3, 8):
+                    O.set_threads(nt)
+                    out, n = O.bucket_mul_mt(v, r["buckets"], r["bucket.stats"], r["probes"], i, o, eff)
+                    assert n == ref["n_selected"]
+                    assert rel_err(out, ref["out64"]) < 1e-5
+            finally:
+                O.set_threads(before)
