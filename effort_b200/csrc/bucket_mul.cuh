@@ -479,15 +479,9 @@ bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
     }
 
     // the cutoff is computed by the first kCutWarps warps (cutoff.cuh, group path)
-#ifdef EFFORT_CUT_OLD
-    constexpr int PER = (EFFORT_PROBES_MAX + NT - 1) / NT;
-    uint16_t prb[PER];
-    if (!pb.cutoff_in) load_probes(pb.probes, e_no, pb.n_probes, prb, keep);
-#else
     const bool cut_thread = !pb.cutoff_in && tid < kCutThreads;
     GroupProbes prb;
     if (cut_thread) group_load_probes(pb.probes + (size_t)e_no * pb.n_probes, pb.n_probes, tid, prb, keep);
-#endif
     // everything above read only constant weight metadata: under PDL it overlaps the previous kernel's tail.
     zero_my_tile<SLOTS, VEC, NW>(sv.tiles);  // while those loads are in flight
     EFFORT_TRACE(1);
@@ -510,12 +504,6 @@ bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
     if (pb.cutoff_in) {
         cutoff = *pb.cutoff_in;
     } else {
-#ifdef EFFORT_CUT_OLD
-        float vals[PER];
-        score_loaded<NORM>(pb.v_cut, prb, pb.n_probes, vals, pb.norm_w, denom);
-        EFFORT_TRACE(3);
-        cutoff = block_bisect_cutoff<NW>(vals, pb.n_probes, pb.q, hdr.cut, nullptr, nullptr);
-#else
         if (cut_thread) {
             GroupProducts gp;
             group_score<NORM>(pb.v_cut, prb, pb.n_probes, tid, gp, pb.norm_w, denom);
@@ -524,7 +512,6 @@ bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
         }
         __syncthreads();
         cutoff = hdr.cut.result;
-#endif
     }
     if (pb.cutoff_out && lb == 0 && tid == 0) *pb.cutoff_out = cutoff;
     EFFORT_TRACE(6);
@@ -629,246 +616,6 @@ bucket_mul_fused_kernel(const __grid_constant__ MulBatch batch) {
     EFFORT_TRACE(9);
 
     // 4. CTA partial (tile layout)
-    reduce_tiles_to_partial<SLOTS, VEC, NW>(sv.tiles, g, pb.partial + (size_t)lb * L::kTileFloats);
-    EFFORT_TRACE(10);
-}
-
-// ---- fused kernel, overlapped variant ---------------------------------------------------------------
-// Same result as bucket_mul_fused_kernel; the difference is WHEN rows start to stream.  The bisection's upper
-// bracket maxBound only ever falls and the final cutoff never exceeds it, so after a few iterations every row
-// with  maxBound < 1e5*stat*|v|  is already certain to be selected (87 % of the finally selected rows after 6
-// iterations on Mistral-shaped data, 98 % after 8).  After kLevels1 iterations the CTA splits:
-//   selectors (warps 0..3) take over all 4096 products (through shared memory) and finish the exact bisection;
-//   streamers (the other warps) build the list of certain rows and stream them meanwhile;
-// they meet at a named barrier, the remaining rows (cutoff < f <= bound1) are listed and streamed by all warps.
-// Requirements (checked on the host, else the plain kernel runs): input-major rows, all ranks loaded,
-// 4096 probes, at most 2 input dims per streamer thread.
-constexpr int kSelWarps = 4;
-constexpr int kLevels1 = 64;  // 64: all of phase A by every warp; only phase B overlaps the streaming
-constexpr int kOvlInputsPerThread = 2;
-
-template <int SLOTS, int VEC, int NW>
-__host__ __device__ inline size_t overlap_smem_bytes(int list_cap) {
-    return MulSmem<SLOTS, VEC, NW>::bytes(list_cap) + EFFORT_PROBES_MAX * sizeof(float);
-}
-
-template <int SLOTS, int VEC, int U, int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
-bucket_mul_overlap_kernel(const __grid_constant__ MulBatch batch) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    using L = MulSmem<SLOTS, VEC, NW>;
-    constexpr int NT = NW * 32;
-    constexpr int NS = NW - kSelWarps, NST = NS * 32;          // streamer warps / threads
-    constexpr int PERA = EFFORT_PROBES_MAX / NT;               // products per thread while all warps bisect
-    constexpr int PERS = EFFORT_PROBES_MAX / (kSelWarps * 32); // products per selector thread afterwards
-    constexpr int PR = (SLOTS == 16) ? 16 : 8;                 // ranks per input dim
-    constexpr int KIN = kOvlInputsPerThread;
-    const MulSmemView<NW> sv = carve_smem<SLOTS, VEC, NW>(smem_raw);
-    MulSmemHeader<NW>& hdr = *sv.hdr;
-    int pi = 0;
-#pragma unroll
-    for (int k = 1; k < kMulBatchMax; k++) pi += (k < batch.n && (int)blockIdx.x >= batch.cta_begin[k]) ? 1 : 0;
-    const MulProblem& pb = batch.p[pi];
-    const int lb = (int)blockIdx.x - batch.cta_begin[pi];
-    float* xs = reinterpret_cast<float*>(sv.list + pb.list_cap);  // [4096] products, after the list
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool is_sel = warp < kSelWarps;
-    const int st = tid - kSelWarps * 32;  // streamer thread index (negative for selectors)
-    pdl_trigger();
-    if (pb.exp_no) pdl_wait();
-    const uint32_t e_no = pb.exp_no ? *pb.exp_no : 0u;
-    const MulGeom g = pb.g;
-    const int slice = lb % g.CS, rsp = lb / g.CS;
-    const uint64_t keep = l2_policy_evict_last();
-    EFFORT_TRACE(0);
-    zero_my_tile<SLOTS, VEC, NW>(sv.tiles);
-
-    // streamers: prefetch the stats of their input dims (constant metadata: legal before pdl_wait)
-    const int n_in = (pb.in > rsp) ? (pb.in - 1 - rsp) / g.RS + 1 : 0;
-    float stat[KIN][PR];
-    float vin[KIN];
-#pragma unroll
-    for (int k = 0; k < KIN; k++) {
-        vin[k] = 0.f;
-#pragma unroll
-        for (int r = 0; r < PR; r++) stat[k][r] = 0.f;
-        const int j = st + k * NST;
-        if (!is_sel && j < n_in) {
-            const int i = rsp + j * g.RS;
-            if constexpr (SLOTS == 16) {
-                const uint4* sp = reinterpret_cast<const uint4*>(pb.st16 + ((size_t)e_no * pb.in + i) * 16);
-                const uint4 s0 = ldg_keep_u4(sp, keep), s1 = ldg_keep_u4(sp + 1, keep);
-                const uint32_t ws[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-                for (int q2 = 0; q2 < 8; q2++) {
-                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ws[q2]));
-                    stat[k][2 * q2] = f.x;
-                    stat[k][2 * q2 + 1] = f.y;
-                }
-            } else {
-                const uint4* sp = reinterpret_cast<const uint4*>(pb.st32 + ((size_t)e_no * pb.in + i) * 8);
-                const uint4 s0 = ldg_keep_u4(sp, keep), s1 = ldg_keep_u4(sp + 1, keep);
-                const uint32_t ws[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-                for (int r = 0; r < 8; r++) stat[k][r] = __uint_as_float(ws[r]);
-            }
-        }
-    }
-    pdl_wait();
-#pragma unroll
-    for (int k = 0; k < KIN; k++) {
-        const int j = st + k * NST;
-        if (!is_sel && j < n_in) vin[k] = pb.v[rsp + j * g.RS];
-    }
-    EFFORT_TRACE(2);
-
-    // all warps: score the probes and run the first kLevels1 iterations of the bisection
-    float vals[PERA];
-    score_probes(pb.v_cut, pb.probes, e_no, pb.n_probes, vals, keep);
-    EFFORT_TRACE(3);
-    BisectState bs;
-    bisect_init(vals, hdr.cut, bs);
-    const int effort = pb.n_probes - pb.q;
-    const bool done1 = bisect_rounds<PERA, NW, 0>(vals, bs, effort, hdr.cut, warp, kLevels1);
-    // stage-1 bound: rows with bound1 < f are certain.  If the loop is already over this is the cutoff itself.
-    const float bound1 = done1 ? bs.newBound : bs.maxBound;
-    if (!done1) {
-#pragma unroll
-        for (int k = 0; k < PERA; k++) xs[tid + k * NT] = vals[k];
-    }
-    __syncthreads();
-    EFFORT_TRACE(5);
-
-    auto row_of = [&](int i, int rho) -> size_t { return ((size_t)e_no * pb.in + i) * PR + rho; };
-    unsigned m1[KIN];
-    int n_list1 = 0;
-    if (is_sel) {
-        if (!done1) {
-            float sv32[PERS];
-#pragma unroll
-            for (int k = 0; k < PERS; k++) sv32[k] = xs[tid + k * (kSelWarps * 32)];
-            const bool done2 = bisect_rounds<PERS, kSelWarps, 1>(sv32, bs, effort, hdr.cut, warp, 1 << 30);
-            bisect_finish<PERS, kSelWarps, 1>(sv32, bs, effort, hdr.cut, warp, done2);
-        } else if (tid == 0) {
-            hdr.cut.result = bs.newBound;
-        }
-#pragma unroll
-        for (int k = 0; k < KIN; k++) m1[k] = 0u;
-        EFFORT_TRACE(6);
-    } else {
-        // ---- stage 1: list + stream the certain rows (streamers only, named barrier 3) ----
-        int base = 0;
-#pragma unroll
-        for (int k = 0; k < KIN; k++) {
-            const int j = st + k * NST;
-            unsigned m = 0u;
-#pragma unroll
-            for (int r = 0; r < PR; r++)
-                if (j < n_in && row_selected(bound1, stat[k][r], vin[k])) m |= 1u << r;
-            m1[k] = m;
-            const int c = __popc(m);
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            if (lane == 31) hdr.warp_cnt[warp] = incl;
-            group_bar(3, NST);
-            int pre = 0, tot = 0;
-#pragma unroll
-            for (int w = kSelWarps; w < NW; w++) {
-                const int wc = hdr.warp_cnt[w];
-                pre += (w < warp) ? wc : 0;
-                tot += wc;
-            }
-            int pos = base + pre + incl - c;
-            if (c) {
-                const int i = rsp + j * g.RS;
-                while (m) {
-                    const int rho = __ffs(m) - 1;
-                    m &= m - 1;
-                    float val = vin[k];
-                    if constexpr (SLOTS != 16) {
-                        float stv = 0.f;
-#pragma unroll
-                        for (int r2 = 0; r2 < PR; r2++) stv = (r2 == rho) ? stat[k][r2] : stv;
-                        val = __fmul_rn(val, stv);  // Q4 payload is v*avg (bucketMulQ4.metal:51)
-                    }
-                    sv.list[pos++] = make_uint2(__float_as_uint(val), (uint32_t)(row_of(i, rho) * (size_t)pb.C));
-                }
-            }
-            base += tot;
-            group_bar(3, NST);
-        }
-        n_list1 = base;
-        EFFORT_TRACE(8);
-        stream_rows<SLOTS, VEC, U>(sv.list, n_list1, pb.bk, pb.C, slice, g,
-                                   sv.tiles_saddr + (uint32_t)warp * L::kTileBytes, warp - kSelWarps, NS);
-    }
-    group_bar(2, NT);  // selectors have the cutoff, streamers are done with stage 1 (and with the list)
-    const float cutoff = hdr.cut.result;
-    if (pb.cutoff_out && lb == 0 && tid == 0) *pb.cutoff_out = cutoff;
-    EFFORT_TRACE(7);
-
-    // ---- stage 2: the rows between the cutoff and the stage-1 bound, all warps ----
-    int n_list2 = 0;
-    if (!done1) {
-        int base = 0;
-#pragma unroll
-        for (int k = 0; k < KIN; k++) {
-            const int j = st + k * NST;
-            unsigned m = 0u;
-            if (!is_sel) {
-#pragma unroll
-                for (int r = 0; r < PR; r++)
-                    if (j < n_in && row_selected(cutoff, stat[k][r], vin[k])) m |= 1u << r;
-                m &= ~m1[k];
-            }
-            const int c = __popc(m);
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            if (lane == 31) hdr.warp_cnt[warp] = incl;
-            __syncthreads();
-            int pre = 0, tot = 0;
-#pragma unroll
-            for (int w = 0; w < NW; w++) {
-                const int wc = hdr.warp_cnt[w];
-                pre += (w < warp) ? wc : 0;
-                tot += wc;
-            }
-            int pos = base + pre + incl - c;
-            if (c) {
-                const int i = rsp + j * g.RS;
-                while (m) {
-                    const int rho = __ffs(m) - 1;
-                    m &= m - 1;
-                    float val = vin[k];
-                    if constexpr (SLOTS != 16) {
-                        float stv = 0.f;
-#pragma unroll
-                        for (int r2 = 0; r2 < PR; r2++) stv = (r2 == rho) ? stat[k][r2] : stv;
-                        val = __fmul_rn(val, stv);
-                    }
-                    sv.list[pos++] = make_uint2(__float_as_uint(val), (uint32_t)(row_of(i, rho) * (size_t)pb.C));
-                }
-            }
-            base += tot;
-            __syncthreads();
-        }
-        n_list2 = base;
-        stream_rows<SLOTS, VEC, U>(sv.list, n_list2, pb.bk, pb.C, slice, g,
-                                   sv.tiles_saddr + (uint32_t)warp * L::kTileBytes, warp, NW);
-    }
-    // rows selected by this CTA: stage 1 (known to the streamers) + stage 2 (known to everyone)
-    if (tid == kSelWarps * 32 && pb.sel_counts && slice == 0) pb.sel_counts[rsp] = (uint32_t)(n_list1 + n_list2);
-    __syncthreads();
-    EFFORT_TRACE(9);
     reduce_tiles_to_partial<SLOTS, VEC, NW>(sv.tiles, g, pb.partial + (size_t)lb * L::kTileFloats);
     EFFORT_TRACE(10);
 }

@@ -38,12 +38,6 @@ struct __align__(16) CutoffSmem {
     int n_inside;
     float result;
     int loops;
-#ifdef EFFORT_CUTOFF_DIRECT  // direct method (block_cutoff_direct), study only
-    unsigned hist[2048];   // products per 16-code bin of the 15-bit bf16 key
-    int sub[5][16];        // per target rank: products per code inside its bin
-    int wsum[32];
-    int tbin[5], trank[5];
-#endif
 };
 
 struct BisectState {
@@ -557,158 +551,23 @@ __device__ __forceinline__ void group_cutoff(const GroupProducts& gp, int n_prob
     }
 }
 
-// ---- direct method -----------------------------------------------------------------------------------
+// ---- why five order statistics are enough -----------------------------------------------------------------
 // The bisection never looks at the products themselves, only at count(b) = #{products > b}, and then only
 //   (1) count(b) < k          <=>  b >= T_k                      (T_j = j-th largest product, k = 4096 - q)
 //   (2) count(b) == k         <=>  T_{k+1} <= b < T_k
 //   (3) |maxCount - minCount| < 3, which can only hold while both counts are within 3 of k.
 // All three are decided exactly by the capped count  c'(b) = (k-3) + sum_{j=k-2..k+2} [T_j > b]
-// (= clamp(count(b), k-3, k+2)), with the 4096 / 0 start literals capped the same way.  So the whole loop is
-// a scalar recurrence over five order statistics: two histogram passes over the 4096 products (2048 bins of 16
-// bf16 codes, then the 16 codes of each target bin) find T_{k-2..k+2} exactly -- ties of any multiplicity
-// included -- and ONE warp replays the reference iterations (same bisect_step, same loop count) with five
-// compares per iteration instead of a block-wide count.  Bit-identical to the iterative path (tests).
-#ifdef EFFORT_CUTOFF_DIRECT
-template <int PER>
-__device__ __forceinline__ float block_cutoff_direct(const float (&vals)[PER], int n_probes, int q, CutoffSmem& sm,
-                                                     int* loops_out) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = blockDim.x, nwarps = NT >> 5;
-    const int B = 2048 / NT;  // bins per thread in the scan (NT = 512 or 1024)
-    const int k = n_probes - q;
-    // S0: zero the histograms; min/max partials (bucketMul.metal:155-181)
-    for (int b = tid; b < 2048; b += NT) sm.hist[b] = 0u;
-    if (tid < 80) (&sm.sub[0][0])[tid] = 0;
-    if (tid < 5) sm.tbin[tid] = -1;  // a rank beyond the number of countable (non-NaN) products has no bin
-    float tmin = 999.f, tmax = -999.f;
-#pragma unroll
-    for (int j = 0; j < PER; j++)
-        if (vals[j] >= 0.f) { tmin = fminf(tmin, vals[j]); tmax = fmaxf(tmax, vals[j]); }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
-        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-    }
-    if (lane == 0) { sm.red_min[warp] = tmin; sm.red_max[warp] = tmax; }
-    __syncthreads();
-    // S1: coarse histogram
-#pragma unroll
-    for (int j = 0; j < PER; j++)
-        if (vals[j] >= 0.f) atomicAdd(&sm.hist[__float_as_uint(vals[j]) >> 20], 1u);  // (bits>>16)>>4
-    __syncthreads();
-    // S2: prefix over bins in DESCENDING order; locate the bins of ranks k-2..k+2
-    {
-        unsigned c[4];
-        unsigned ts = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            c[j] = (j < B) ? sm.hist[2047 - (tid * B + j)] : 0u;
-            ts += c[j];
-        }
-        unsigned incl = ts;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) sm.wsum[warp] = (int)incl;
-        __syncthreads();
-        unsigned before = incl - ts;
-        for (int w = 0; w < warp; w++) before += (unsigned)sm.wsum[w];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (j < B && c[j]) {
-#pragma unroll
-                for (int ri = 0; ri < 5; ri++) {
-                    const int r = k - 2 + ri;
-                    if (r >= 1 && (unsigned)r > before && (unsigned)r <= before + c[j]) {
-                        sm.tbin[ri] = 2047 - (tid * B + j);
-                        sm.trank[ri] = r - (int)before;
-                    }
-                }
-            }
-            before += c[j];
-        }
-    }
-    __syncthreads();
-    // S3: fine histogram of each target bin (ranks outside 1..n_probes have no bin: tbin stays unmatched)
-    {
-        int tb[5];
-#pragma unroll
-        for (int ri = 0; ri < 5; ri++) {
-            const int r = k - 2 + ri;
-            tb[ri] = (r >= 1 && r <= n_probes) ? sm.tbin[ri] : -1;
-        }
-#pragma unroll
-        for (int j = 0; j < PER; j++) {
-            if (vals[j] >= 0.f) {
-                const unsigned key = __float_as_uint(vals[j]) >> 16;
-#pragma unroll
-                for (int ri = 0; ri < 5; ri++)
-                    if ((int)(key >> 4) == tb[ri]) atomicAdd(&sm.sub[ri][key & 15u], 1);
-            }
-        }
-    }
-    __syncthreads();
-    // S4: one warp resolves T_{k-2..k+2} and replays the reference loop
-    if (warp == 0) {
-        float T[5];
-#pragma unroll
-        for (int ri = 0; ri < 5; ri++) {
-            const int r = k - 2 + ri;
-            float t;
-            if (r < 1) t = __int_as_float(0x7F800000);   // count(b) >= r always
-            else if (r > n_probes || sm.tbin[ri] < 0) t = -1.f;  // never
-            else {
-                int need = sm.trank[ri], code = 15, acc = 0;
-                for (; code > 0; code--) {
-                    acc += sm.sub[ri][code];
-                    if (acc >= need) break;
-                }
-                t = __uint_as_float((((unsigned)sm.tbin[ri] << 4) | (unsigned)code) << 16);
-            }
-            T[ri] = t;
-        }
-        float gmin = (lane < nwarps) ? sm.red_min[lane] : 999.f;
-        float gmax = (lane < nwarps) ? sm.red_max[lane] : -999.f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
-            gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-        }
-        BisectState s;
-        s.minBound = bf16_round(gmin);  // 999 -> 1000 through the bfloat tgMin (:172-181)
-        s.maxBound = bf16_round(gmax);
-        s.newBound = (s.minBound + s.maxBound) / 2;
-        s.loops = 0;
-        s.minCount = min(4096, k + 2);  // capped start literals (:197, :168-169)
-        s.maxCount = max(0, k - 3);
-        bool done = false;
-        while (!done) {
-            s.loops++;
-            const float b = s.newBound;
-            const int c = (k - 3) + (T[0] > b ? 1 : 0) + (T[1] > b ? 1 : 0) + (T[2] > b ? 1 : 0) +
-                          (T[3] > b ? 1 : 0) + (T[4] > b ? 1 : 0);
-            done = bisect_step(s, c, k);
-        }
-        if (lane == 0) { sm.result = s.newBound; sm.loops = s.loops; }
-    }
-    __syncthreads();
-    if (loops_out && tid == 0) *loops_out = sm.loops;
-    return sm.result;
-}
+// (= clamp(count(b), k-3, k+2)), with the 4096 / 0 start literals capped the same way: this is what group_cutoff's
+// scalar replay evaluates (tests/test_oracle.py checks it against the literal loop, from the start and from a
+// mid-way state).  A variant that found the T_j with two shared-memory histogram passes instead of phase A was
+// measured slower (atomic contention on the few occupied bins) and removed; it is in the history (commit 7979362).
 
-#endif
-
-// Whole-CTA bisection (stand-alone kernel and the non-overlapped fused path).
+// Whole-CTA bisection (stand-alone kernel when n_probes > 4096).
 template <int NWB, int PER>
 __device__ __forceinline__ float block_bisect_cutoff(const float (&vals)[PER], int n_probes, int q,
                                                      CutoffSmem& sm, int* loops_out,
                                                      unsigned long long* trace = nullptr) {
     (void)trace;
-#ifdef EFFORT_CUTOFF_DIRECT  // measured slower than the iterative path on B200 (shared-memory atomics + a ~30-step
-                             // scalar replay cost ~6 us vs ~5.5 us); kept for study, exactness covered by the same tests
-    if ((2048 % blockDim.x) == 0 && blockDim.x >= 512) return block_cutoff_direct(vals, n_probes, q, sm, loops_out);
-#endif
     BisectState s;
     bisect_init(vals, sm, s);
     const int effort = n_probes - q;  // :154
@@ -735,34 +594,6 @@ __device__ __forceinline__ void score_probes(const float* __restrict__ v, const 
             if constexpr (NORM) vi = (vi / denom) * __half2float(norm_w[i]);  // fused rmsNorm*w on load
             float x = __fmul_rn(__fmul_rn(kCutoffScale, vi), p);
             vals[k] = bf16_round(fabsf(x));
-        } else {
-            vals[k] = -1.f;
-        }
-    }
-}
-
-// Same in two halves so that the (constant) probes can be fetched before a PDL wait and the activations after.
-template <int PER>
-__device__ __forceinline__ void load_probes(const __half* __restrict__ probes, uint32_t exp_no, int n_probes,
-                                            uint16_t (&pr)[PER], uint64_t keep) {
-#pragma unroll
-    for (int k = 0; k < PER; k++) {
-        const int i = threadIdx.x + k * blockDim.x;
-        pr[k] = (i < n_probes) ? ldg_keep_u16(probes + (size_t)exp_no * n_probes + i, keep) : (uint16_t)0;
-    }
-}
-template <bool NORM = false, int PER>
-__device__ __forceinline__ void score_loaded(const float* __restrict__ v, const uint16_t (&pr)[PER], int n_probes,
-                                             float (&vals)[PER], const __half* __restrict__ norm_w = nullptr,
-                                             float denom = 1.f) {
-#pragma unroll
-    for (int k = 0; k < PER; k++) {
-        const int i = threadIdx.x + k * blockDim.x;
-        if (i < n_probes) {
-            const float p = bf16_round(__half2float(__ushort_as_half(pr[k])));
-            float vi = v[i];
-            if constexpr (NORM) vi = (vi / denom) * __half2float(norm_w[i]);
-            vals[k] = bf16_round(fabsf(__fmul_rn(__fmul_rn(kCutoffScale, vi), p)));
         } else {
             vals[k] = -1.f;
         }

@@ -270,19 +270,6 @@ static int check_mul_args(const effort_ctx* ctx, const float* v, const effort_we
     return EFFORT_OK;
 }
 
-// kernel variants (FP16 kind).  EFFORT_MUL_VARIANT selects one at run time for experiments.
-//   0: 8-byte loads, 8 in flight, 16 warps     1: 8-byte loads, 16 in flight, 16 warps
-//   2: 16-byte loads, 8 in flight, 10 warps
-static int mul_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("EFFORT_MUL_VARIANT");
-        v = e ? atoi(e) : 0;
-        if (v < 0 || v > 2) v = 0;
-    }
-    return v;
-}
-
 static constexpr size_t kMaxSmem = 227 * 1024;
 static bool ring_enabled() {  // EFFORT_RING=1: cp.async ring instead of the register-buffered streaming loop (measured slower)
     static int v = -1;
@@ -290,11 +277,6 @@ static bool ring_enabled() {  // EFFORT_RING=1: cp.async ring instead of the reg
     return v == 1;
 }
 
-static bool overlap_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("EFFORT_OVERLAP"); v = (e && atoi(e) == 1) ? 1 : 0; }  // experimental, off
-    return v == 1;
-}
 
 struct MulCall {  // one problem of a launch group, host side
     MulProblem pb;
@@ -346,26 +328,10 @@ static int launch_fused_batch(MulCall* calls, int n, int n_cta, cudaStream_t str
     if (cta > n_cta) return EFFORT_ESHAPE;
     batch.cta_begin[n] = cta;
     for (int k = 0; k < n; k++) batch.p[k].list_cap = list_cap;
-    // overlapped variant (streams certain rows while the bisection finishes) when its preconditions hold
-    bool overlap = overlap_enabled() && NW > kSelWarps;
-    for (int k = 0; k < n; k++) {
-        const MulProblem& pb = batch.p[k];
-        const int per_cta = (pb.in + pb.g.RS - 1) / pb.g.RS;
-        overlap = overlap && pb.layout == kInputMajor && pb.P == (SLOTS == 16 ? 16 : 8) &&
-                  pb.n_probes == EFFORT_PROBES_MAX && per_cta <= kOvlInputsPerThread * (NW - kSelWarps) * 32 &&
-                  !pb.cutoff_in && !pb.norm_w;
-    }
-    const size_t smem = overlap ? overlap_smem_bytes<SLOTS, VEC, NW>(list_cap) : MulSmem<SLOTS, VEC, NW>::bytes(list_cap);
+    const size_t smem = MulSmem<SLOTS, VEC, NW>::bytes(list_cap);
     if (smem > kMaxSmem) return EFFORT_ESHAPE;
-    static size_t configured = 0, configured_ovl = 0;
-    if (overlap) {
-        if (smem > configured_ovl) {
-            CK(cudaFuncSetAttribute(bucket_mul_overlap_kernel<SLOTS, VEC, U, NW>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured_ovl = smem;
-        }
-        CK(launch_pdl(bucket_mul_overlap_kernel<SLOTS, VEC, U, NW>, dim3(cta), dim3(NW * 32), smem, stream, batch));
-    } else {
+    static size_t configured = 0;
+    {
         bool norm = batch.p[0].norm_w != nullptr;
         for (int k = 1; k < n; k++)
             if ((batch.p[k].norm_w != nullptr) != norm) return EFFORT_EINVAL;  // a group is all-norm or all-plain
@@ -428,11 +394,8 @@ static MulCall make_call(effort_ctx* ctx, const float* v, const effort_weights* 
 }
 
 static int launch_calls(effort_ctx* ctx, MulCall* calls, int n, int kind, bool all_c8, cudaStream_t stream) {
-    if (kind == EFFORT_KIND_FP16) {
-        const int variant = all_c8 ? mul_variant() : 0;  // 16-byte loads need C % 8 == 0
-        (void)variant;
-        return launch_fused_batch<16, 4, 8, 16>(calls, n, ctx->n_sms, stream);
-    }
+    (void)all_c8;  // a 16-byte-load variant (C % 8 == 0) was measured no faster than 8-byte loads and removed
+    if (kind == EFFORT_KIND_FP16) return launch_fused_batch<16, 4, 8, 16>(calls, n, ctx->n_sms, stream);
     return launch_fused_batch<32, 2, 8, 16>(calls, n, ctx->n_sms, stream);
 }
 
