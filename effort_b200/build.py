@@ -35,7 +35,7 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    extra = os.environ.get("EFFORT_NVCC_EXTRA", "").split()   # e.g. -DEFFORT_CUT_OLD for A/B builds
+    extra = os.environ.get("EFFORT_NVCC_EXTRA", "").split()   # extra nvcc flags for A/B builds (tools/ab_op.py + EFFORT_LIB)
     cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     host_cc = "/usr/bin/g++"

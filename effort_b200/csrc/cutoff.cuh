@@ -8,18 +8,19 @@
 // floats (> 1e-5 apart), so the reference spins to its 100-loop cap (one threadgroup, 3 barriers per
 // loop).  The result is still a deterministic function of the inputs, and it is reproduced here
 // BIT-EXACTLY (same cutoff => same selected bucket rows as the oracle's literal restatement), but
-// executed as:
-//   phase A  group-wide counting rounds while more than 128 products lie inside (minBound, maxBound];
-//            every round performs TWO reference iterations: besides the count at the current midpoint it
-//            counts at both midpoints the next iteration could pick ((mid+min)/2 and (max+mid)/2 -- the
-//            same fp32 expressions the reference evaluates), so the second step needs no synchronisation;
-//   phase B  the <=128 inside products are compacted to shared memory and ONE warp finishes with no group
-//            barriers; as soon as everything left inside is one repeated value the count is a step function
-//            of the midpoint and the remaining halvings down to two adjacent floats cost a compare each;
-//   fixpoint once the midpoint stops moving, later loops cannot change the state, so the remaining
+// executed in one of two ways:
+//   group path (group_cutoff, further down): what the fused bucketMul kernel and the stand-alone launch run for
+//            n_probes <= 4096 -- four warps, packed bf16 counting, rank-sort of the bracket, scalar replay;
+//   block-wide path (block_bisect_cutoff): any n_probes <= 8192, all warps of the CTA:
+//     phase A  counting rounds while more than 128 products lie inside (minBound, maxBound]; every round performs
+//              TWO reference iterations: besides the count at the current midpoint it counts at both midpoints
+//              the next iteration could pick ((mid+min)/2 and (max+mid)/2 -- the same fp32 expressions the
+//              reference evaluates), so the second step needs no synchronisation;
+//     phase B  the <=128 inside products are compacted to shared memory and ONE warp finishes with no block
+//              barriers; as soon as everything left inside is one repeated value the count is a step function
+//              of the midpoint and the remaining halvings down to two adjacent floats cost a compare each;
+//   fixpoint (both) once the midpoint stops moving, later loops cannot change the state, so the remaining
 //            iterations up to the reference's 100-loop cap are skipped (loops is reported as 101).
-// The pieces are device functions over a "group" of warps (the whole CTA, or the selector warps of the
-// fused bucketMul kernel, which keep bisecting while the other warps already stream certain rows).
 #pragma once
 #include "common.cuh"
 

@@ -312,7 +312,7 @@ def test_basic_mul_casts_v_to_fp16():
 
 
 # ---------------------------------------------------------------------------------------------------------
-# the derivation the CUDA cutoff relies on (csrc/cutoff.cuh, block_cutoff_direct): the literal bisection only ever
+# the derivation the CUDA cutoff relies on (csrc/cutoff.cuh, "why five order statistics are enough"): the literal bisection only ever
 # needs the capped count (k-3) + sum_{j=k-2..k+2} [T_j > b] of five order statistics
 # ---------------------------------------------------------------------------------------------------------
 def _direct_cutoff(vals, k):
