@@ -67,3 +67,22 @@ def test_argument_validation_needs_no_gpu():
     assert L.effort_bucketize(one, 4096, 2048, one, one, one, None) == -1      # in < 4096
     assert L.effort_bucketize(one, 3008, 4096, one, one, one, None) == -1      # out < 4096 and 4096 % out != 0
     assert L.effort_bucketize(one, 32016, 4096, one, one, one, None) == -1     # > 32000
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under effort_b200/ or include/ may import, load or link it."""
+    import re
+    pkg = os.path.join(ROOT, "effort_b200")
+    offenders = []
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                continue
+            text = open(os.path.join(base, f), errors="replace").read()
+            if re.search(r"^\s*(from|import)\s+oracle\b|liboracle|oracle/|import_module\(.oracle", text, re.M):
+                offenders.append(os.path.join(base, f))
+    assert not offenders, offenders
+    # and the library itself has no dependency on it
+    import subprocess
+    out = subprocess.run(["ldd", os.path.join(pkg, "libeffort_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out
