@@ -228,11 +228,15 @@ int open_file(const std::string& path, std::unique_ptr<StFile>& out) {
         TensorRec r;
         r.dtype = dtype_code(dt->str);  // unsupported types are kept (-1) and refused when asked for
         uint64_t count = 1;
+        const double kMaxExact = 9007199254740992.0;  // 2^53: beyond it a JSON number is not an exact integer
         for (auto& d : sh->arr) {
-            if (d.kind != JVal::kNum || d.num < 0) return EFFORT_EINVAL;
+            if (d.kind != JVal::kNum || !(d.num >= 0) || d.num > kMaxExact) return EFFORT_EINVAL;
             r.shape.push_back((int64_t)d.num);
+            if (d.num != 0 && count > (uint64_t)kMaxExact / (uint64_t)d.num) return EFFORT_EINVAL;  // overflow
             count *= (uint64_t)d.num;
         }
+        for (int k = 0; k < 2; k++)
+            if (off->arr[k].kind != JVal::kNum || !(off->arr[k].num >= 0) || off->arr[k].num > kMaxExact) return EFFORT_EINVAL;
         r.begin = (uint64_t)off->arr[0].num;
         r.end = (uint64_t)off->arr[1].num;
         if (r.end < r.begin || r.end > f->size - f->data_off) return EFFORT_EINVAL;

@@ -146,3 +146,47 @@ def test_bf16_to_f16_all_codes():
     nan = np.isnan(f32)
     assert np.array_equal(dst[~nan], want[~nan])
     assert np.all(np.isnan(dst[nan].view(np.float16)))
+
+
+def test_native_loader_survives_corrupted_headers(tmp_path):
+    """Model files come from outside: a damaged header must produce an error code (or a tensor whose bytes lie inside
+    the mapping), never a crash.  Mutates the header of a valid file byte-wise and field-wise."""
+    import struct
+    from effort_b200._lib import EffortError
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((8, 4)).astype(np.float16)
+    hdr = json.dumps({"x": {"dtype": "F16", "shape": [8, 4], "data_offsets": [0, 64]}, "__metadata__": {"description": "d"}})
+    json.dump({"weight_map": {"x": "f.safetensors"}}, open(tmp_path / "m.safetensors.index.json", "w"))
+
+    def write(h: bytes, data=x.tobytes()):
+        open(tmp_path / "f.safetensors", "wb").write(struct.pack("<Q", len(h)) + h + data)
+
+    def probe():
+        try:
+            a = W.NativeTensorLoader(str(tmp_path), model="m")["x"]
+            assert a.nbytes <= 64
+        except (EffortError, KeyError):
+            pass
+
+    write(hdr.encode())
+    assert np.array_equal(W.NativeTensorLoader(str(tmp_path), model="m")["x"], x)
+    for field in ('"shape": [8, 4]', '"data_offsets": [0, 64]', '"dtype": "F16"'):
+        for repl in ('"shape": [8, -4]', '"shape": [1e300, 4]', '"shape": [9007199254740993, 9007199254740993]', '"shape": "x"',
+                     '"data_offsets": [64, 0]', '"data_offsets": [0, 1e30]', '"data_offsets": [-8, 56]', '"data_offsets": [0]',
+                     '"dtype": "I64"', '"dtype": 16'):
+            write(hdr.replace(field, repl).encode())
+            probe()
+    raw = bytearray(hdr.encode())
+    for _ in range(1500):
+        m = bytearray(raw)
+        for _ in range(int(rng.integers(1, 4))):
+            m[int(rng.integers(0, len(m)))] = int(rng.integers(0, 256))
+        write(bytes(m))
+        probe()
+    for cut in range(0, len(raw), 7):            # truncated headers / files
+        write(bytes(raw[:cut]))
+        probe()
+        open(tmp_path / "f.safetensors", "wb").write((struct.pack("<Q", len(raw)) + bytes(raw))[: 8 + cut])
+        probe()
+    open(tmp_path / "f.safetensors", "wb").write(struct.pack("<Q", 2 ** 63) + bytes(raw))   # absurd header size
+    probe()
