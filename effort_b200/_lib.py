@@ -44,6 +44,7 @@ SIGNATURES = {
     "effort_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
     "effort_comm_destroy": (C.c_int, [vp]),
     "effort_comm_p2p_local_handle": (C.c_int, [vp, vp]),
+    "effort_comm_p2p_disable": (C.c_int, [vp]),
     "effort_comm_p2p_connect": (C.c_int, [vp, vp, C.c_int, C.c_int]),
     "effort_comm_all_reduce": (C.c_int, [vp, vp, C.c_size_t, vp]),
     "effort_comm_all_gather": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),

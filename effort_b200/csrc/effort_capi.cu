@@ -818,6 +818,12 @@ extern "C" int effort_comm_p2p_connect(effort_ctx_t* ctx, const void* handles, i
     return EFFORT_OK;
 }
 
+extern "C" int effort_comm_p2p_disable(effort_ctx_t* ctx) {
+    if (!ctx) return EFFORT_EINVAL;
+    ctx->p2p_ready = false;  // the mappings stay until the context is destroyed; the token loop takes the NCCL path
+    return EFFORT_OK;
+}
+
 template <int MODE>
 static int p2p_launch(effort_ctx* ctx, int site, const float* send, float* out, size_t count, cudaStream_t s) {
     if (site < 0 || site >= kP2PSites || count * 8 * (size_t)ctx->comm_world > kP2PSiteBytes)  // 8-byte {value, seq} packets

@@ -41,7 +41,16 @@ def init_comm(ctx: "ops.Context", rank: int, world: int) -> None:
         allh = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allh, mine)
         blob = b"".join(bytes(x.cpu().numpy().tobytes()) for x in allh)
-        check(L.effort_comm_p2p_connect(ctx._h, blob, rank, world), "effort_comm_p2p_connect")
+        ok = 1 if L.effort_comm_p2p_connect(ctx._h, blob, rank, world) == 0 else 0
+        # peer mapping can be refused (no CUDA IPC between the devices / in the container): the decision to use the
+        # peer-memory kernels must be the same on every rank, so agree on it and fall back to NCCL together
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            check(L.effort_comm_p2p_disable(ctx._h), "effort_comm_p2p_disable")
+            if rank == 0:
+                import warnings
+                warnings.warn("effort_b200: CUDA-IPC peer mapping unavailable, tensor-parallel exchanges use NCCL")
         dist.barrier()
 
 

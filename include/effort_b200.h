@@ -172,6 +172,8 @@ int effort_comm_destroy(effort_ctx_t* ctx);
  * returns its 64-byte cudaIpcMemHandle_t; connect: takes all ranks' handles (world x 64 bytes, rank order). */
 int effort_comm_p2p_local_handle(effort_ctx_t* ctx, void* handle64_out);
 int effort_comm_p2p_connect(effort_ctx_t* ctx, const void* handles, int rank, int world);
+/* back to NCCL for the exchanges (call on EVERY rank when any rank failed to connect: the choice must be collective) */
+int effort_comm_p2p_disable(effort_ctx_t* ctx);
 /* in-place sum all-reduce / all-gather of fp32 device buffers over the ctx communicator (test + building block) */
 int effort_comm_all_reduce(effort_ctx_t* ctx, float* buf_dev, size_t count, void* stream);
 int effort_comm_all_gather(effort_ctx_t* ctx, const float* send_dev, float* recv_dev, size_t send_count, void* stream);
