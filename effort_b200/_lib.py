@@ -24,6 +24,9 @@ SIGNATURES = {
     "effort_last_cuda_error": (C.c_char_p, []),
     "effort_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "effort_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "effort_ctx_set_cutoff_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "effort_ctx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "effort_ctx_error_flag": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint), vp]),
     "effort_weights_create": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_uint, vp, C.POINTER(C.c_void_p)]),
     "effort_weights_destroy": (C.c_int, [C.c_void_p]),
@@ -60,6 +63,7 @@ SIGNATURES = {
     "effort_model_bucket_bytes": (C.c_size_t, [vp]),
     "effort_model_set_graphs": (C.c_int, [vp, C.c_int]),
     "effort_model_set_fused_glue": (C.c_int, [vp, C.c_int]),
+    "effort_model_set_chain": (C.c_int, [vp, C.c_int]),
     "effort_launch_count": (C.c_uint64, []),
     "effort_last_selected": (C.c_int, [vp, C.POINTER(C.c_uint32), vp]),
     "effort_loader_open": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),

@@ -31,6 +31,8 @@ namespace effort {
 enum RowLayout : int {
     kInputMajor = 0,  // row(e,i,rho) = (e*in + i)*P + rho      (device repack; Q4 native order)
     kRankMajor = 1,   // row(e,i,rho) = e*P*in + rho*in + i      (reference FP16 order, convert.metal:96)
+    kSliceMajor = 2,  // [e][column slice s][i][rho][W_s columns]: the rows an input selects in a slice are CONTIGUOUS
+                      // (bucket_mul_v2 only); stats as kInputMajor.  W = slice width, W_s = min(W, C - s*W)
 };
 
 struct MulGeom {

@@ -108,6 +108,25 @@ __global__ void repack_rows_kernel(const uint16_t* __restrict__ src, int n_exper
     }
 }
 
+// bucket rows -> slice-major [e][slice][i][rho][W_s]; src is rank-major (src_rank_major) or input-major.  One thread per
+// 16-byte piece (C % 8 == 0, W % 8 == 0).
+__global__ void repack_slices_kernel(const uint16_t* __restrict__ src, int n_experts, int in, int P, int C, int W,
+                                     int src_rank_major, uint16_t* __restrict__ dst) {
+    const size_t pieces_per_row = (size_t)C / 8;
+    const size_t n = (size_t)n_experts * in * P * pieces_per_row;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const size_t r = t / pieces_per_row;            // destination-independent logical row (e, i, rho)
+    const int c0 = (int)(t % pieces_per_row) * 8;   // first column of the piece
+    const size_t e = r / ((size_t)in * P), rem = r % ((size_t)in * P);
+    const size_t i = rem / P, rho = rem % P;
+    const size_t srow = src_rank_major ? e * (size_t)in * P + rho * in + i : r;
+    const int sl = c0 / W, cw = c0 % W;
+    const int Ws = (C - sl * W) < W ? (C - sl * W) : W;
+    const size_t d = e * (size_t)in * P * C + (size_t)in * P * ((size_t)sl * W) + (i * P + rho) * (size_t)Ws + cw;
+    *reinterpret_cast<uint4*>(dst + d) = *reinterpret_cast<const uint4*>(src + srow * C + c0);
+}
+
 // ---- dense comparator: basicMul (helpers/mps.swift:14-47, matrix.metal:150-162) ----------------------
 // v is cast to fp16 first (mps.swift:19); fp16 x fp16 products accumulated in fp32.  One warp per output
 // row, 16-byte weight loads, v staged once per CTA in shared memory as fp16-rounded floats.

@@ -9,13 +9,31 @@ namespace effort {
 
 // fetchRow16to32 (aux.metal:355-363): x = float(tok_embeddings[token]); also the per-block partial sums of x^2 that
 // the first layer's fused rmsNorm-on-load consumes (sumsq[gridDim.x], may be null).
+// buffers a kernel of the decode chain clears for a LATER producer that accumulates into them (bucket_mul_v2 adds its
+// result into `out` with reductions; the consumer of the previous use has finished by stream order)
+struct ZeroList {
+    float* p[6];
+    int n[6];
+};
+__device__ __forceinline__ void zero_lists(const ZeroList& z, int part, int parts, int tid, int nt) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        if (!z.p[k]) continue;
+        const int n4 = z.n[k] >> 2;  // lengths are multiples of 4
+        float4* q = reinterpret_cast<float4*>(z.p[k]);
+        for (int i = part * nt + tid; i < n4; i += parts * nt) q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 __global__ void __launch_bounds__(1024)
-embed_kernel(const int* __restrict__ token, const __half* __restrict__ emb, int dim, float* __restrict__ x,
-             float* __restrict__ sumsq) {
+embed_kernel(const int* __restrict__ token, const __half* __restrict__ emb, int dim, int vocab, float* __restrict__ x,
+             float* __restrict__ sumsq, const ZeroList zl) {
     __shared__ float red[32];
     pdl_trigger();
     pdl_wait();
-    const int t = *token;
+    zero_lists(zl, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x);
+    int t = *token;
+    t = (t < 0 || t >= vocab) ? 0 : t;  // never index the table with a garbage token (e.g. argmax over NaN logits)
     float ss = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += gridDim.x * blockDim.x) {
         const float xv = __half2float(emb[(size_t)t * dim + i]);
@@ -87,8 +105,8 @@ __global__ void silu_mul_kernel(const float* __restrict__ x1, const float* __res
 __global__ void __launch_bounds__(256)
 attention_kernel(const float* __restrict__ xq, const float* __restrict__ xk, const float* __restrict__ xv,
                  float* __restrict__ kcache, float* __restrict__ vcache,  // [max_seq][n_kv][128]
-                 const int* __restrict__ pos_dev, int n_heads, int n_kv, float theta, int tp_head0,
-                 float* __restrict__ attn_out) {
+                 const int* __restrict__ pos_dev, int n_heads, int n_kv, float theta, int max_seq,
+                 float* __restrict__ attn_out, const ZeroList zl) {
     constexpr int HD = 128;
     __shared__ float q[HD];
     __shared__ float acc_s[8][HD];
@@ -96,9 +114,10 @@ attention_kernel(const float* __restrict__ xq, const float* __restrict__ xk, con
     const int h = blockIdx.x, kvh = h / (n_heads / n_kv);
     pdl_trigger();
     pdl_wait();
-    const int pos = *pos_dev;
+    int pos = *pos_dev;
+    pos = pos < 0 ? 0 : (pos >= max_seq ? max_seq - 1 : pos);  // backstop: the host refuses steps past max_seq
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    (void)tp_head0;
+    zero_lists(zl, blockIdx.x, gridDim.x, tid, blockDim.x);
     // rope(q) into smem; the first head of each KV group also ropes k and appends k/v to the cache
     if (tid < HD) {
         const int j = tid & 63;
@@ -165,7 +184,7 @@ argmax_advance_kernel(const float* __restrict__ logits, int n, int* __restrict__
     pdl_trigger();
     pdl_wait();
     float best = -INFINITY;
-    int idx = 0x7fffffff;
+    int idx = 0x7fffffff;  // all-NaN logits leave it there: clamped to 0 below
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const float x = logits[i];
         if (x > best || (x == best && i < idx)) { best = x; idx = i; }
@@ -186,7 +205,99 @@ argmax_advance_kernel(const float* __restrict__ logits, int n, int* __restrict__
             const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
             if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
         }
-        if (threadIdx.x == 0) { *next_token = idx; *pos_dev = *pos_dev + 1; }
+        if (threadIdx.x == 0) { *next_token = (idx < 0 || idx >= n) ? 0 : idx; *pos_dev = *pos_dev + 1; }
+    }
+}
+
+// ---- fused head: final rmsNorm * w on load, dense lm_head GEMV (basicMul, helpers/mps.swift:14-47), greedy argmax ----
+// (runNetwork.swift:206-209 + mpsTopK index 0, :235-257).  One warp per vocabulary row; every CTA keeps its best
+// (logit, index) and the last CTA to finish (atomic ticket) reduces the per-CTA candidates -- lowest index wins ties, the
+// same rule as argmax_advance_kernel -- writes the next token and advances the position.  v_norm_w == null: v is used as is.
+__global__ void __launch_bounds__(256)
+head_kernel(const float* __restrict__ h, const __half* __restrict__ norm_w, float eps, const __half* __restrict__ W,
+            int out, int in, int row0, float* __restrict__ logits, float2* __restrict__ cand, unsigned* __restrict__ ticket,
+            int* __restrict__ next_token, int* __restrict__ pos_dev, int do_argmax) {
+    extern __shared__ float vs[];
+    __shared__ float red[8];
+    __shared__ float bestv[8];
+    __shared__ int besti[8];
+    __shared__ int is_last;
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float denom = 1.f;
+    if (norm_w) {
+        float ss = 0.f;
+        for (int i = threadIdx.x; i < in; i += blockDim.x) { const float x = h[i]; ss += x * x; }
+        ss = warp_sum_f(ss);
+        if (lane == 0) red[warp] = ss;
+        __syncthreads();
+        float t = (lane < 8) ? red[lane] : 0.f;
+        t = warp_sum_f(t);
+        denom = sqrtf(t / (float)in + eps);
+    }
+    for (int i = threadIdx.x; i < in; i += blockDim.x) {
+        float x = h[i];
+        if (norm_w) x = (x / denom) * __half2float(norm_w[i]);
+        vs[i] = __half2float(__float2half_rn(x));  // v is cast to fp16 first (mps.swift:19)
+    }
+    __syncthreads();
+    float best = -INFINITY;
+    int bidx = 0x7fffffff;
+    for (int o = blockIdx.x * 8 + warp; o < out; o += gridDim.x * 8) {
+        const __half* row = W + (size_t)o * in;
+        float acc = 0.f;
+        for (int c = lane * 8; c < in; c += 256) {
+            const uint4 d = ldg_stream_u4(row + c);
+            const uint32_t ws[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ws[j]));
+                acc = fmaf(vs[c + 2 * j], f.x, acc);
+                acc = fmaf(vs[c + 2 * j + 1], f.y, acc);
+            }
+        }
+        acc = warp_sum_f(acc);
+        if (lane == 0) logits[o] = acc;
+        const int gi = row0 + o;
+        if (acc > best || (acc == best && gi < bidx)) { best = acc; bidx = gi; }
+    }
+    if (!do_argmax) return;
+    if (lane == 0) { bestv[warp] = best; besti[warp] = bidx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++)
+            if (bestv[w] > best || (bestv[w] == best && besti[w] < bidx)) { best = bestv[w]; bidx = besti[w]; }
+        cand[blockIdx.x] = make_float2(best, __int_as_float(bidx));
+        __threadfence();
+        const unsigned t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    best = -INFINITY;
+    bidx = 0x7fffffff;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+        float2 c;
+        asm volatile("ld.volatile.global.v2.f32 {%0,%1}, [%2];" : "=f"(c.x), "=f"(c.y) : "l"(cand + b));
+        const int ci = __float_as_int(c.y);
+        if (c.x > best || (c.x == best && ci < bidx)) { best = c.x; bidx = ci; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    if (lane == 0) { bestv[warp] = best; besti[warp] = bidx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < 8; w++)
+            if (bestv[w] > best || (bestv[w] == best && besti[w] < bidx)) { best = bestv[w]; bidx = besti[w]; }
+        *next_token = (bidx == 0x7fffffff) ? 0 : bidx;  // all-NaN logits: token 0, never an out-of-range index
+        *pos_dev = *pos_dev + 1;
+        *ticket = 0u;  // re-armed for the next token (graph replay)
     }
 }
 

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "bucket_mul.cuh"
+#include "bucket_mul_v2.cuh"
 #include "comm.cuh"
 #include "convert.cuh"
 #include "cutoff.cuh"
@@ -77,6 +78,15 @@ struct effort_ctx {
     bool have_dispatch = false;
     int dispatch_kind = 0;
     unsigned long long* trace = nullptr;  // [n_sms][16] when EFFORT_TRACE=1
+    // round-2 fused kernel (bucket_mul_v2.cuh)
+    unsigned* v2_sync = nullptr;          // [kMaxBatch][kV2MaxSlices][2] arrive/depart counters (overwrite protocol)
+    unsigned* v2_err = nullptr;           // [1] set by a kernel whose overwrite barrier timed out
+    int cutoff_mode = 0;                  // EFFORT_CUTOFF_SELECT / EFFORT_CUTOFF_BISECT
+    int stage_mode = 0;                   // 0 = cp.async (LDGSTS) ring, 1 = cp.async.bulk (TMA) ring
+    int engine = 2;                       // 2 = bucket_mul_v2_kernel, 1 = round-1 fused kernel + integrate
+    int dynamic = 1;                      // v2 streaming: units from a shared counter (1) or static round robin (0)
+    int last_rs[8] = {0};                 // row splits of the last v2 launch per batch slot (effort_last_selected)
+    bool last_was_v2 = false;
     void* comm = nullptr;                  // ncclComm_t
     int comm_rank = 0, comm_world = 1;
     unsigned char* p2p_local = nullptr;    // this rank's symmetric buffer
@@ -85,6 +95,9 @@ struct effort_ctx {
 };
 
 static constexpr int kMaxBatch = 8;
+static constexpr int kV2MaxSlices = 64;
+
+static bool default_slice_major();
 
 extern "C" int effort_version(void) { return EFFORT_B200_VERSION; }
 extern "C" const char* effort_last_cuda_error(void) { return g_cuda_err.c_str(); }
@@ -124,11 +137,43 @@ extern "C" int effort_ctx_create(int device, effort_ctx_t** ctx_out) {
     CK(cudaMemset(c->sizes, 0, sizeof(uint32_t) * (4 + kMaxBatch)));
     CK(cudaMemset(c->cutoff, 0, sizeof(float) * kMaxBatch));
     CK(cudaMemset(c->loops, 0, sizeof(int)));
+    CK(cudaMalloc(&c->v2_sync, sizeof(unsigned) * kMaxBatch * kV2MaxSlices * 2));
+    CK(cudaMemset(c->v2_sync, 0, sizeof(unsigned) * kMaxBatch * kV2MaxSlices * 2));
+    CK(cudaMalloc(&c->v2_err, sizeof(unsigned)));
+    CK(cudaMemset(c->v2_err, 0, sizeof(unsigned)));
+    CK(cudaMalloc(&c->sel_counts, sizeof(uint32_t) * kMaxBatch * c->n_sms));  // fixed size: graphs keep the pointer
+    CK(cudaMemset(c->sel_counts, 0, sizeof(uint32_t) * kMaxBatch * c->n_sms));
+    c->sel_cap = (size_t)kMaxBatch * c->n_sms;
+    { const char* e = getenv("EFFORT_CUTOFF"); if (e && !strcmp(e, "bisect")) c->cutoff_mode = 1; }
+    { const char* e = getenv("EFFORT_STAGE"); if (e && !strcmp(e, "bulk")) c->stage_mode = 1; }
+    { const char* e = getenv("EFFORT_ENGINE"); if (e && atoi(e) == 1) c->engine = 1; }
+    { const char* e = getenv("EFFORT_DYN"); if (e && atoi(e) == 0) c->dynamic = 0; }
     if (getenv("EFFORT_TRACE")) {
         CK(cudaMalloc(&c->trace, sizeof(unsigned long long) * 16 * c->n_sms));
         CK(cudaMemset(c->trace, 0, sizeof(unsigned long long) * 16 * c->n_sms));
     }
     *ctx_out = c;
+    return EFFORT_OK;
+}
+
+extern "C" int effort_ctx_set_cutoff_mode(effort_ctx_t* c, int mode) {
+    if (!c || (mode != EFFORT_CUTOFF_SELECT && mode != EFFORT_CUTOFF_BISECT)) return EFFORT_EINVAL;
+    c->cutoff_mode = mode;
+    return EFFORT_OK;
+}
+
+extern "C" int effort_ctx_set_option(effort_ctx_t* c, const char* name, int value) {
+    if (!c || !name) return EFFORT_EINVAL;
+    if (!strcmp(name, "engine")) { if (value != 1 && value != 2) return EFFORT_EINVAL; c->engine = value; return EFFORT_OK; }
+    if (!strcmp(name, "stage")) { if (value != 0 && value != 1) return EFFORT_EINVAL; c->stage_mode = value; return EFFORT_OK; }
+    if (!strcmp(name, "dynamic")) { if (value != 0 && value != 1) return EFFORT_EINVAL; c->dynamic = value; return EFFORT_OK; }
+    return EFFORT_EINVAL;
+}
+
+extern "C" int effort_ctx_error_flag(effort_ctx_t* c, unsigned* flag_out, void* stream) {
+    if (!c || !flag_out) return EFFORT_EINVAL;
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    CK(cudaMemcpy(flag_out, c->v2_err, sizeof(unsigned), cudaMemcpyDeviceToHost));
     return EFFORT_OK;
 }
 
@@ -146,6 +191,11 @@ extern "C" int effort_ctx_destroy(effort_ctx_t* c) {
     if (!c) return EFFORT_OK;
     cudaFree(c->cutoff); cudaFree(c->loops); cudaFree(c->sizes); cudaFree(c->dispatch);
     cudaFree(c->chunk_counts); cudaFree(c->partial); cudaFree(c->sel_counts);
+    cudaFree(c->trace); cudaFree(c->v2_sync); cudaFree(c->v2_err);
+    for (int p = 0; p < 16; p++)
+        if (c->p2p_peer[p] && c->p2p_peer[p] != (void*)c->p2p_local) cudaIpcCloseMemHandle(c->p2p_peer[p]);
+    cudaFree(c->p2p_local);
+    effort_comm_destroy(c);
     delete c;
     return EFFORT_OK;
 }
@@ -220,7 +270,8 @@ extern "C" int effort_weights_create(const void* buckets_dev, const void* stats_
         w->owned += (size_t)n_experts * EFFORT_PROBES_COUNT * sizeof(__half);
         if (kind == EFFORT_KIND_FP16) {
             const bool repack = !(flags & EFFORT_WEIGHTS_NO_REPACK);
-            w->layout = repack ? kInputMajor : kRankMajor;
+            const bool slice_major = repack && ((flags & EFFORT_WEIGHTS_SLICE_MAJOR) || default_slice_major()) && (w->C % 8) == 0;
+            w->layout = repack ? (slice_major ? kSliceMajor : kInputMajor) : kRankMajor;
             CK(cudaMalloc(&w->st16, rows * sizeof(__half)));
             w->owned += rows * sizeof(__half);
             repack_stats_fp16_kernel<<<(unsigned)((rows + TB - 1) / TB), TB, 0, stream>>>(
@@ -229,8 +280,15 @@ extern "C" int effort_weights_create(const void* buckets_dev, const void* stats_
             if (repack) {
                 CK(cudaMalloc(&w->bk_own, rows * (size_t)w->C * 2));
                 w->owned += rows * (size_t)w->C * 2;
-                repack_rows_kernel<<<(unsigned)((rows * 32 + TB - 1) / TB), TB, 0, stream>>>(
-                    w->buckets, n_experts, in_dim, percent_load, w->C, w->bk_own);
+                if (slice_major) {
+                    const size_t pieces = rows * (size_t)(w->C / 8);
+                    const int W = w->C < 128 ? w->C : 128;
+                    repack_slices_kernel<<<(unsigned)((pieces + TB - 1) / TB), TB, 0, stream>>>(
+                        w->buckets, n_experts, in_dim, percent_load, w->C, W, 1, w->bk_own);
+                } else {
+                    repack_rows_kernel<<<(unsigned)((rows * 32 + TB - 1) / TB), TB, 0, stream>>>(
+                        w->buckets, n_experts, in_dim, percent_load, w->C, w->bk_own);
+                }
                 LAUNCHED();
             }
         } else {
@@ -261,6 +319,12 @@ static inline int effort_q(double effort, int n_probes) {
     // let q = Int(Double(probesCount-1)*(1-effort))   bucketMul.swift:39
     double x = (double)(n_probes - 1) * (1.0 - effort);
     return (int)x;
+}
+
+static bool default_slice_major() {  // EFFORT_LAYOUT=slice: device copy in the slice-major layout (v2 engine only)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EFFORT_LAYOUT"); v = (e && !strcmp(e, "slice")) ? 1 : 0; }
+    return v == 1;
 }
 
 static int check_mul_args(const effort_ctx* ctx, const float* v, const effort_weights* w, const float* out,
@@ -368,6 +432,121 @@ static int launch_fused_batch(MulCall* calls, int n, int n_cta, cudaStream_t str
     return EFFORT_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// round-2 engine: bucket_mul_v2_kernel (one launch per group, no integrate)
+// ---------------------------------------------------------------------------------------------------
+struct V2Call {  // one problem of a launch group, host side
+    const float* v = nullptr;       // input / residual stream (norm_w != null) / x1 (v2 != null)
+    const float* v2 = nullptr;      // x3 -> input = silu(x1) * x3
+    const float* v_cut = nullptr;   // row shards: first 4096 entries of the full input
+    const __half* norm_w = nullptr; // input = rmsNorm(v) * norm_w
+    float norm_eps = 1e-5f;
+    const effort_weights* w = nullptr;
+    const uint32_t* exp_no = nullptr;
+    float* out = nullptr;
+    double effort = 0.25;
+    int out_mode = kOutOverwrite;
+};
+
+static bool v2_supported(const effort_weights* w) {
+    if (!w->buckets && !w->bk_own) return false;
+    if (w->layout == kSliceMajor && w->kind != EFFORT_KIND_FP16) return false;
+    if (w->n_probes != EFFORT_PROBES_MAX) return false;
+    if (w->kind == EFFORT_KIND_FP16) return (w->C % 8) == 0 && w->P <= 16;
+    return (w->C % 8) == 0 && w->P <= 8;
+}
+
+template <int SLOTS, int VEC>
+static int launch_v2_batch(effort_ctx* ctx, const V2Call* calls, int n, int slot0, cudaStream_t stream) {
+    if (n < 1 || n > kMulBatchMax) return EFFORT_EINVAL;
+    constexpr int D = 4;
+    const int n_cta = ctx->n_sms;
+    V2Batch batch{};
+    batch.n = n;
+    double total_bytes = 0;
+    int cs_sum = 0;
+    for (int k = 0; k < n; k++) {
+        const effort_weights* w = calls[k].w;
+        total_bytes += (double)w->in * w->C;
+        cs_sum += make_geom<VEC>(w->C, n_cta).CS;
+    }
+    if (cs_sum > n_cta) return EFFORT_ESHAPE;
+    int cta = 0, list_cap = 0;
+    for (int k = 0; k < n; k++) {
+        const V2Call& c = calls[k];
+        const effort_weights* w = c.w;
+        MulGeom g = make_geom<VEC>(w->C, n_cta);
+        if (g.CS > kV2MaxSlices) return EFFORT_ESHAPE;
+        const double share = (double)w->in * w->C / total_bytes;
+        int rs = (int)((n_cta - (cs_sum - g.CS)) * share / g.CS);
+        if (n == 1) rs = n_cta / g.CS;
+        if (rs < 1) rs = 1;
+        if (rs > w->in) rs = w->in;
+        V2Problem& pb = batch.p[k];
+        const bool norm = c.norm_w != nullptr, silu = c.v2 != nullptr;
+        if (norm && silu) return EFFORT_EINVAL;
+        if ((norm || silu) && c.v_cut) return EFFORT_EINVAL;        // glue-on-load needs the whole input locally
+        if (norm && w->in != 8 * kV2Threads) return EFFORT_ESHAPE;   // the fused rmsNorm sums exactly 4096 entries
+        if (!c.v_cut && w->in < EFFORT_PROBES_MAX) return EFFORT_ESHAPE;
+        pb.v = c.v; pb.v2 = c.v2; pb.v_cut = c.v_cut ? c.v_cut : c.v; pb.norm_w = c.norm_w; pb.norm_eps = c.norm_eps;
+        pb.st16 = w->st16; pb.st32 = w->st32; pb.bk = w->fast_bk(); pb.probes = w->probes; pb.exp_no = c.exp_no;
+        pb.out = c.out;
+        pb.sync = ctx->v2_sync + (size_t)(slot0 + k) * kV2MaxSlices * 2;
+        pb.sel_counts = ctx->sel_counts + (size_t)(slot0 + k) * ctx->n_sms;
+        pb.cutoff_out = ctx->cutoff + slot0 + k;
+        pb.err_flag = ctx->v2_err;
+        pb.trace = ctx->trace;
+        pb.in = w->in; pb.C = w->C; pb.P = w->P; pb.q = effort_q(c.effort, w->n_probes); pb.layout = w->layout;
+        pb.out_mode = c.out_mode;
+        pb.CS = g.CS; pb.RS = rs; pb.W = (g.CS == 1) ? w->C : 32 * VEC; pb.R = g.R; pb.lpr = g.lpr;
+        const int per_cta = (w->in + rs - 1) / rs;
+        const int cap = (per_cta < kV2MaxInputs ? per_cta : kV2MaxInputs) * V2Smem<SLOTS, VEC>::kUnitsPerInput;
+        list_cap = cap > list_cap ? cap : list_cap;
+        batch.cta_begin[k] = cta;
+        cta += g.CS * rs;
+        ctx->last_rs[slot0 + k] = rs;
+    }
+    if (cta > n_cta) return EFFORT_ESHAPE;
+    batch.cta_begin[n] = cta;
+    batch.list_cap = (list_cap + 63) & ~63;
+    using L = V2Smem<SLOTS, VEC>;
+    bool bulk = ctx->stage_mode == 1;
+    // one bulk copy per unit needs the unit's rows contiguous in HBM: the slice-major device layout
+    for (int k = 0; k < n; k++) bulk = bulk && calls[k].w->layout == kSliceMajor;
+    batch.dynamic = ctx->dynamic;
+    const size_t smem = L::bytes(batch.list_cap, D);
+    if (smem > kMaxSmem) return EFFORT_ESHAPE;
+    auto go = [&](auto kernel) -> int {
+        static bool configured[64] = {false};  // per kernel instantiation and device
+        const int dev = ctx->device & 63;
+        if (!configured[dev]) {
+            CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+            configured[dev] = true;
+        }
+        CK(launch_pdl(kernel, dim3(cta), dim3(kV2Threads), smem, stream, batch));
+        return EFFORT_OK;
+    };
+    int rc;
+    const bool bisect = ctx->cutoff_mode == 1;
+    if (bisect) rc = bulk ? go(bucket_mul_v2_kernel<SLOTS, VEC, kCutBisect, kStageBulk, D>)
+                          : go(bucket_mul_v2_kernel<SLOTS, VEC, kCutBisect, kStageLdgsts, D>);
+    else rc = bulk ? go(bucket_mul_v2_kernel<SLOTS, VEC, kCutSelect, kStageBulk, D>)
+                   : go(bucket_mul_v2_kernel<SLOTS, VEC, kCutSelect, kStageLdgsts, D>);
+    if (rc) return rc;
+    LAUNCHED();
+    ctx->last_was_v2 = true;
+    return EFFORT_OK;
+}
+
+static int launch_v2(effort_ctx* ctx, const V2Call* calls, int n, int slot0, cudaStream_t stream) {
+    const int kind = calls[0].w->kind;
+    for (int k = 1; k < n; k++)
+        if (calls[k].w->kind != kind) return EFFORT_EINVAL;
+    if (kind == EFFORT_KIND_FP16) return launch_v2_batch<16, 4>(ctx, calls, n, slot0, stream);
+    return launch_v2_batch<32, 2>(ctx, calls, n, slot0, stream);
+}
+
 // floats of partial scratch one problem needs (upper bound over variants)
 static size_t partial_floats(const effort_ctx* ctx, const effort_weights* w) {
     const int slots = w->kind == EFFORT_KIND_FP16 ? 16 : 32;
@@ -399,19 +578,33 @@ static int launch_calls(effort_ctx* ctx, MulCall* calls, int n, int kind, bool a
     return launch_fused_batch<32, 2, 8, 16>(calls, n, ctx->n_sms, stream);
 }
 
+// Round-1 engine scratch (partial tiles): allocated ONCE at its maximum (kMaxBatch problems of the larger kind) so that
+// captured CUDA graphs never see the pointer change (a later, larger call used to cudaFree it under them).
+static int ensure_mul_scratch(effort_ctx* ctx, size_t, int) {
+    if (ctx->partial) return EFFORT_OK;
+    const size_t need = (size_t)kMaxBatch * ctx->n_sms * 32 * 32 * 8;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    (void)st;
+    return ensure(ctx->partial, ctx->partial_cap, need);
+}
+
 // One fused bucketMul.  slot = scratch slot inside a batch.
 static int enqueue_bucket_mul(effort_ctx* ctx, const float* v, const effort_weights* w, const uint32_t* exp_no,
                               float* out, double effort, int accumulate, int slot, size_t partial_off,
                               cudaStream_t stream) {
+    if (ctx->engine == 2 && v2_supported(w)) {
+        V2Call c;
+        c.v = v; c.w = w; c.exp_no = exp_no; c.out = out; c.effort = effort;
+        c.out_mode = accumulate ? kOutAccumulate : kOutOverwrite;
+        return launch_v2(ctx, &c, 1, slot, stream);
+    }
+    ctx->last_was_v2 = false;
+    int rc = ensure_mul_scratch(ctx, 0, kMaxBatch);
+    if (rc) return rc;
     MulCall c = make_call(ctx, v, w, exp_no, out, effort, accumulate, slot, partial_off);
     return launch_calls(ctx, &c, 1, w->kind, (w->C % 8) == 0, stream);
 }
 
-static int ensure_mul_scratch(effort_ctx* ctx, size_t partial_floats_needed, int slots) {
-    int rc = ensure(ctx->partial, ctx->partial_cap, partial_floats_needed);
-    if (rc) return rc;
-    return ensure(ctx->sel_counts, ctx->sel_cap, (size_t)slots * ctx->n_sms);
-}
 
 // ---------------------------------------------------------------------------------------------------
 // operator entry points
@@ -422,8 +615,6 @@ extern "C" int effort_bucket_mul(effort_ctx_t* ctx, const float* v_dev, const ef
     if (rc) return rc;
     if (w->kind != EFFORT_KIND_FP16) return EFFORT_EINVAL;  // assert(!goQ8...) bucketMul.swift:72
     if (!w->buckets) return EFFORT_ENOTLOADED;
-    rc = ensure_mul_scratch(ctx, partial_floats(ctx, w), kMaxBatch);
-    if (rc) return rc;
     return enqueue_bucket_mul(ctx, v_dev, w, exp_no_dev, out_dev, effort, 0, 0, 0, (cudaStream_t)stream_);
 }
 
@@ -441,8 +632,6 @@ extern "C" int effort_bucket_mul_q4(effort_ctx_t* ctx, const float* v_dev, const
     if (rc) return rc;
     if (w->kind != EFFORT_KIND_Q4) return EFFORT_EINVAL;
     if (!w->buckets) return EFFORT_ENOTLOADED;
-    rc = ensure_mul_scratch(ctx, partial_floats(ctx, w), kMaxBatch);
-    if (rc) return rc;
     // bucketMulQ4 accumulates into out (atomics, bucketMulQ4.metal:89), then calcOutliers (:61)
     rc = enqueue_bucket_mul(ctx, v_dev, w, exp_no_dev, out_dev, effort, 1, 0, 0, (cudaStream_t)stream_);
     if (rc) return rc;
@@ -479,8 +668,9 @@ static int expert_mul_one(effort_ctx* ctx, const effort_mul_args_t& a, int slot,
     const effort_weights* w = a.w;
     if (w->kind == EFFORT_KIND_Q4) {  // expertMul.swift:25-31
         if (w->buckets) {
-            CK(cudaMemsetAsync(a.out_dev, 0, sizeof(float) * w->out, stream));  // out.zero()
-            int rc = enqueue_bucket_mul(ctx, a.v_dev, w, a.exp_no_dev, a.out_dev, a.effort, 1, slot, partial_off, stream);
+            const bool v2 = ctx->engine == 2 && v2_supported(w);  // the v2 kernel zeroes `out` itself (overwrite mode)
+            if (!v2) CK(cudaMemsetAsync(a.out_dev, 0, sizeof(float) * w->out, stream));  // out.zero()
+            int rc = enqueue_bucket_mul(ctx, a.v_dev, w, a.exp_no_dev, a.out_dev, a.effort, v2 ? 0 : 1, slot, partial_off, stream);
             if (rc) return rc;
             return enqueue_outliers(a.v_dev, w, a.out_dev, stream);
         }
@@ -500,9 +690,38 @@ extern "C" int effort_expert_mul_batch(effort_ctx_t* ctx, const effort_mul_args_
         if (rc) return rc;
         total += partial_floats(ctx, args[k].w);
     }
-    int rc = ensure_mul_scratch(ctx, total, kMaxBatch);
+    int rc = 0;
+    if (ctx->engine == 2) {
+        // FP16 problems with buckets loaded go into ONE launch of the v2 kernel (up to kMulBatchMax); everything else
+        // (Q4: overwrite + outliers; dense fallback; shapes the v2 kernel does not take) is enqueued one by one in order.
+        V2Call group[kMulBatchMax];
+        int ng = 0, slot0 = 0;
+        auto flush = [&]() -> int {
+            if (!ng) return EFFORT_OK;
+            int r = launch_v2(ctx, group, ng, slot0, stream);
+            ng = 0;
+            return r;
+        };
+        for (int k = 0; k < n; k++) {
+            const effort_weights* w = args[k].w;
+            if (w->kind == EFFORT_KIND_FP16 && w->buckets && v2_supported(w)) {
+                if (ng == kMulBatchMax && (rc = flush())) return rc;
+                if (ng == 0) slot0 = k;
+                V2Call& c = group[ng++];
+                c = V2Call{};
+                c.v = args[k].v_dev; c.v_cut = args[k].v_cutoff_dev; c.w = w; c.exp_no = args[k].exp_no_dev;
+                c.out = args[k].out_dev; c.effort = args[k].effort; c.out_mode = kOutOverwrite;
+            } else {
+                if ((rc = flush())) return rc;
+                if ((rc = expert_mul_one(ctx, args[k], k, 0, stream))) return rc;
+            }
+        }
+        return flush();
+    }
+    ctx->last_was_v2 = false;
+    rc = ensure_mul_scratch(ctx, total, kMaxBatch);
     if (rc) return rc;
-    // FP16 problems with buckets loaded go into ONE launch group (up to kMulBatchMax); everything else
+    // round-1 engine: FP16 problems with buckets loaded go into ONE launch group (up to kMulBatchMax); everything else
     // (Q4: out.zero() + outliers; dense fallback) is enqueued one by one in order.
     MulCall group[kMulBatchMax];
     int ng = 0;
@@ -643,6 +862,14 @@ extern "C" int effort_read_dispatch(effort_ctx_t* ctx, float* dispatch_host, siz
 extern "C" int effort_last_selected(effort_ctx_t* ctx, uint32_t* n_selected, void* stream_) {
     if (!ctx || !n_selected) return EFFORT_EINVAL;
     CK(cudaStreamSynchronize((cudaStream_t)stream_));
+    if (ctx->last_was_v2) {  // v2 kernel: one count per row split of batch slot 0
+        std::vector<uint32_t> c((size_t)ctx->last_rs[0]);
+        CK(cudaMemcpy(c.data(), ctx->sel_counts, sizeof(uint32_t) * c.size(), cudaMemcpyDeviceToHost));
+        uint32_t t = 0;
+        for (uint32_t x : c) t += x;
+        *n_selected = t;
+        return EFFORT_OK;
+    }
     CK(cudaMemcpy(n_selected, ctx->sizes + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return EFFORT_OK;
 }
@@ -894,6 +1121,14 @@ struct effort_model {
           *attn_ffn_out = nullptr, *fxn = nullptr, *x1 = nullptr, *x3 = nullptr, *x2 = nullptr, *ffn_out = nullptr,
           *out_normed = nullptr, *logits = nullptr;
     int *pos = nullptr, *token = nullptr, *next = nullptr;
+    // round-2 chain: the GEMV outputs are ACCUMULATED (reductions) into double-buffered vectors that an earlier kernel of
+    // the chain has cleared (layer parity picks the buffer)
+    float *xq2[2] = {nullptr, nullptr}, *xk2[2] = {nullptr, nullptr}, *xv2[2] = {nullptr, nullptr};
+    float *x1_2[2] = {nullptr, nullptr}, *x3_2[2] = {nullptr, nullptr};
+    float2* head_cand = nullptr;   // per-CTA argmax candidates of head_kernel
+    unsigned* head_ticket = nullptr;
+    int host_pos = 0;              // tokens decoded since the last reset (bounds the KV cache)
+    int chain = 2;                 // 2 = fused v2 chain (5 launches per layer), 1 = one kernel per reference op
     int *h_token = nullptr, *h_next = nullptr;  // pinned
     float* h_logits = nullptr;                  // pinned
     std::map<int, cudaGraphExec_t> graphs;      // keyed by q = Int(4095*(1-effort))
@@ -947,6 +1182,14 @@ extern "C" int effort_model_create(effort_ctx_t* ctx, const effort_model_config_
         (rc = model_alloc(m, m->sumsq_b, 1024)))
         return rc;
     { const char* e = getenv("EFFORT_FUSE_GLUE"); m->fuse_glue = e && atoi(e) == 1; }
+    { const char* e = getenv("EFFORT_CHAIN"); if (e && atoi(e) == 1) m->chain = 1; }
+    for (int b = 0; b < 2; b++) {
+        if ((rc = model_alloc(m, m->xq2[b], cfg->dim)) || (rc = model_alloc(m, m->xk2[b], kvd)) ||
+            (rc = model_alloc(m, m->xv2[b], kvd)) || (rc = model_alloc(m, m->x1_2[b], cfg->hidden_dim)) ||
+            (rc = model_alloc(m, m->x3_2[b], cfg->hidden_dim)))
+            return rc;
+    }
+    if ((rc = model_alloc(m, m->head_cand, (size_t)ctx->n_sms * 8)) || (rc = model_alloc(m, m->head_ticket, 1))) return rc;
     CK(cudaMallocHost(&m->h_token, sizeof(int)));
     CK(cudaMallocHost(&m->h_next, sizeof(int)));
     CK(cudaMallocHost(&m->h_logits, sizeof(float) * cfg->vocab));
@@ -990,12 +1233,15 @@ extern "C" int effort_model_set_head(effort_model_t* m, const void* norm_dev, co
     if (!m || !norm_dev || !output_core_dev || !tok_embeddings_dev) return EFFORT_EINVAL;
     m->norm = (const __half*)norm_dev; m->out_core = (const __half*)output_core_dev;
     m->emb = (const __half*)tok_embeddings_dev;
+    for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);  // captured graphs hold the old pointers
+    m->graphs.clear();
     return EFFORT_OK;
 }
 
 extern "C" int effort_model_reset(effort_model_t* m, void* stream) {
     if (!m) return EFFORT_EINVAL;
     CK(cudaMemsetAsync(m->pos, 0, sizeof(int), (cudaStream_t)stream));
+    m->host_pos = 0;
     return EFFORT_OK;
 }
 
@@ -1015,6 +1261,16 @@ extern "C" int effort_model_set_fused_glue(effort_model_t* m, int enable) {
     return EFFORT_OK;
 }
 
+extern "C" int effort_model_set_chain(effort_model_t* m, int chain) {
+    if (!m || (chain != 1 && chain != 2)) return EFFORT_EINVAL;
+    if (m->chain != chain) {
+        for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
+        m->graphs.clear();
+    }
+    m->chain = chain;
+    return EFFORT_OK;
+}
+
 extern "C" const float* effort_model_logits(const effort_model_t* m) { return m ? m->logits : nullptr; }
 extern "C" const int32_t* effort_model_next_token(const effort_model_t* m) { return m ? m->next : nullptr; }
 extern "C" size_t effort_model_bucket_bytes(const effort_model_t* m) {
@@ -1026,6 +1282,88 @@ extern "C" size_t effort_model_bucket_bytes(const effort_model_t* m) {
     return b;
 }
 
+
+// ---- round-2 decode chain (single GPU, FP16 buckets): 5 launches per layer ------------------------------------------
+//   [q,k,v]  one v2 launch, rmsNorm(h)*attn_norm applied on load, results accumulated into the parity buffers
+//   attention (+ clears the buffers of the next layer)
+//   wo       v2, plain input, accumulates straight into the residual stream h        (h.add(by:), runNetwork.swift:172)
+//   [w1,w3]  one v2 launch, rmsNorm(h)*ffn_norm on load
+//   w2       v2, input = silu(x1)*x3 computed on load, accumulates into h             (runNetwork.swift:181-183)
+// then head_kernel: final norm on load + lm_head + argmax + position advance.
+static bool model_all_fp16_v2(const effort_model* m) {
+    for (const auto& l : m->layers)
+        for (const effort_weights* w : {l.wq, l.wk, l.wv, l.wo, l.w1, l.w2, l.w3})
+            if (!w || w->kind != EFFORT_KIND_FP16 || !w->buckets || !v2_supported(w)) return false;
+    return m->cfg.dim == 8 * kV2Threads;
+}
+
+static int enqueue_head(effort_model* m, const float* h, const __half* norm_w, const __half* core, int rows, int row0,
+                        float* logits, bool do_argmax, cudaStream_t s) {
+    const auto& c = m->cfg;
+    const size_t smem = (size_t)c.dim * sizeof(float);
+    static bool configured[64] = {false};
+    if (smem > 48 * 1024 && !configured[m->ctx->device & 63]) {
+        CK(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[m->ctx->device & 63] = true;
+    }
+    int grid = (rows + 7) / 8;
+    const int max_grid = m->ctx->n_sms * 8;
+    if (grid > max_grid) grid = max_grid;
+    CK(launch_pdl(head_kernel, dim3(grid), dim3(256), smem, s, h, norm_w, c.norm_eps, core, rows, c.dim, row0, logits,
+                  m->head_cand, m->head_ticket, m->next, m->pos, do_argmax ? 1 : 0));
+    LAUNCHED();
+    return EFFORT_OK;
+}
+
+static int model_enqueue_token_v2(effort_model* m, double effort, cudaStream_t s) {
+    const auto& c = m->cfg;
+    effort_ctx* ctx = m->ctx;
+    const int kvd = c.n_kv_heads * c.head_dim;
+    int rc;
+    {   // the first layer accumulates into parity-0 buffers: cleared here (whatever the layer count's parity)
+        ZeroList z{};
+        z.p[0] = m->xq2[0]; z.n[0] = c.dim; z.p[1] = m->xk2[0]; z.n[1] = kvd; z.p[2] = m->xv2[0]; z.n[2] = kvd;
+        z.p[3] = m->x1_2[0]; z.n[3] = c.hidden_dim; z.p[4] = m->x3_2[0]; z.n[4] = c.hidden_dim;
+        CK(launch_pdl(embed_kernel, dim3(4), dim3(1024), 0, s, (const int*)m->token, m->emb, c.dim, c.vocab, m->h,
+                      (float*)nullptr, z));
+        LAUNCHED();
+    }
+    for (int li = 0; li < c.n_layers; li++) {
+        auto& l = m->layers[li];
+        const int b = li & 1, nb = b ^ 1;
+        V2Call qkv[3];
+        const effort_weights* wqkv[3] = {l.wq, l.wk, l.wv};
+        float* oqkv[3] = {m->xq2[b], m->xk2[b], m->xv2[b]};
+        for (int k = 0; k < 3; k++) {
+            qkv[k].v = m->h; qkv[k].norm_w = l.attn_norm; qkv[k].norm_eps = c.norm_eps; qkv[k].w = wqkv[k];
+            qkv[k].out = oqkv[k]; qkv[k].effort = effort; qkv[k].out_mode = kOutAccumulate;
+        }
+        if ((rc = launch_v2(ctx, qkv, 3, 0, s))) return rc;
+        ZeroList z{};
+        z.p[0] = m->xq2[nb]; z.n[0] = c.dim; z.p[1] = m->xk2[nb]; z.n[1] = kvd; z.p[2] = m->xv2[nb]; z.n[2] = kvd;
+        z.p[3] = m->x1_2[nb]; z.n[3] = c.hidden_dim; z.p[4] = m->x3_2[nb]; z.n[4] = c.hidden_dim;
+        CK(launch_pdl(attention_kernel, dim3(c.n_heads), dim3(256), 0, s, (const float*)m->xq2[b], (const float*)m->xk2[b],
+                      (const float*)m->xv2[b], l.kc, l.vc, (const int*)m->pos, c.n_heads, c.n_kv_heads, c.rope_theta, c.max_seq,
+                      m->attn, z));
+        LAUNCHED();
+        V2Call wo;
+        wo.v = m->attn; wo.w = l.wo; wo.out = m->h; wo.effort = effort; wo.out_mode = kOutAccumulate;
+        if ((rc = launch_v2(ctx, &wo, 1, 0, s))) return rc;
+        V2Call w13[2];
+        const effort_weights* ww[2] = {l.w1, l.w3};
+        float* o13[2] = {m->x1_2[b], m->x3_2[b]};
+        for (int k = 0; k < 2; k++) {
+            w13[k].v = m->h; w13[k].norm_w = l.ffn_norm; w13[k].norm_eps = c.norm_eps; w13[k].w = ww[k];
+            w13[k].out = o13[k]; w13[k].effort = effort; w13[k].out_mode = kOutAccumulate;
+        }
+        if ((rc = launch_v2(ctx, w13, 2, 0, s))) return rc;
+        V2Call w2;
+        w2.v = m->x1_2[b]; w2.v2 = m->x3_2[b]; w2.w = l.w2; w2.out = m->h; w2.effort = effort; w2.out_mode = kOutAccumulate;
+        if ((rc = launch_v2(ctx, &w2, 1, 0, s))) return rc;
+    }
+    return enqueue_head(m, m->h, m->norm, m->out_core, c.vocab, 0, m->logits, true, s);
+}
+
 // enqueue one token (no graph logic).  token lives in m->token (device).  With tp_size = G > 1 this rank holds
 // heads [rank*32/G, ...) and hidden columns [rank*14336/G, ...): q/k/v/w1/w3 are column shards (no exchange),
 // wo/w2 are row shards: all-gather the first 4096 dims of their input (cutoff parity), all-reduce the output.
@@ -1035,9 +1373,12 @@ static int model_enqueue_token(effort_model* m, double effort, cudaStream_t s) {
     const int G = c.tp_size;
     const int dim_l = c.dim / G, hid_l = c.hidden_dim / G, heads_l = c.n_heads / G, kv_l = c.n_kv_heads / G;
     if (!m->norm) return EFFORT_ESTATE;
-    CK(launch_pdl(embed_kernel, dim3(4), dim3(1024), 0, s, (const int*)m->token, m->emb, c.dim, m->h, m->sumsq_a));
-    LAUNCHED();
     int rc;
+    const bool v2_chain = G == 1 && m->chain == 2 && ctx->engine == 2 && model_all_fp16_v2(m);
+    if (v2_chain) return model_enqueue_token_v2(m, effort, s);
+    CK(launch_pdl(embed_kernel, dim3(4), dim3(1024), 0, s, (const int*)m->token, m->emb, c.dim, c.vocab, m->h, m->sumsq_a,
+                  ZeroList{}));
+    LAUNCHED();
     if (G == 1 && m->fuse_glue && m->layers[0].wq && m->layers[0].wq->kind == EFFORT_KIND_FP16 &&
         m->layers[0].wq->buckets) {
         // Fused glue (single GPU, FP16): rmsNorm*w is applied on load inside the bucketMul kernels from per-block
@@ -1058,7 +1399,7 @@ static int model_enqueue_token(effort_model* m, double effort, cudaStream_t s) {
             for (auto& mc : qkv) with_norm(mc, l.attn_norm, m->sumsq_a, n_sumsq);
             if ((rc = launch_calls(ctx, qkv, 3, EFFORT_KIND_FP16, false, s))) return rc;
             CK(launch_pdl(attention_kernel, dim3(heads_l), dim3(256), 0, s, (const float*)m->xq, (const float*)m->xk,
-                          (const float*)m->xv, l.kc, l.vc, (const int*)m->pos, heads_l, kv_l, c.rope_theta, 0, m->attn));
+                          (const float*)m->xv, l.kc, l.vc, (const int*)m->pos, heads_l, kv_l, c.rope_theta, c.max_seq, m->attn, ZeroList{}));
             LAUNCHED();
             MulCall wo = make_call(ctx, m->attn, l.wo, nullptr, m->h, effort, 0, 0, 0);
             wo.mode = kIntResidual; wo.sumsq = m->sumsq_b;  // h += wo(attn); sumsq_b = partial sum(h^2)
@@ -1102,7 +1443,7 @@ static int model_enqueue_token(effort_model* m, double effort, cudaStream_t s) {
                                     {m->h_norm, l.wv, nullptr, m->xv, effort, nullptr}};
         if ((rc = effort_expert_mul_batch(ctx, qkv, 3, s))) return rc;
         CK(launch_pdl(attention_kernel, dim3(heads_l), dim3(256), 0, s, (const float*)m->xq, (const float*)m->xk,
-                      (const float*)m->xv, l.kc, l.vc, (const int*)m->pos, heads_l, kv_l, c.rope_theta, 0, m->attn));
+                      (const float*)m->xv, l.kc, l.vc, (const int*)m->pos, heads_l, kv_l, c.rope_theta, c.max_seq, m->attn, ZeroList{}));
         LAUNCHED();
         const float* wo_cut = nullptr;
         if (G > 1) {
@@ -1168,6 +1509,8 @@ extern "C" int effort_model_step(effort_model_t* m, const int32_t* token_dev, do
     cudaStream_t s = (cudaStream_t)stream_;
     if (!m) return EFFORT_EINVAL;
     if (!(effort >= 0.0 && effort <= 1.0)) return EFFORT_EINVAL;
+    if (m->host_pos >= m->cfg.max_seq) return EFFORT_ESTATE;  // KV cache full (the reference bounds the loop by maxSeqLen)
+    m->host_pos++;
     CK(cudaMemcpyAsync(m->token, token_dev ? (const void*)token_dev : (const void*)m->next, sizeof(int),
                        cudaMemcpyDeviceToDevice, s));
     const int key = effort_q(effort, EFFORT_PROBES_COUNT);

@@ -221,6 +221,10 @@ class DecodeModel:
     def set_fused_glue(self, enable: bool):
         check(self._L.effort_model_set_fused_glue(self._h, 1 if enable else 0), "effort_model_set_fused_glue")
 
+    def set_chain(self, chain: int):
+        """2 = fused round-2 chain (5 launches per layer, default), 1 = one kernel per reference op."""
+        check(self._L.effort_model_set_chain(self._h, int(chain)), "effort_model_set_chain")
+
     def step(self, token: Optional[torch.Tensor] = None, effort: float = 0.25):
         """Enqueue one decode step (token: device int32[1]; None = previous prediction)."""
         check(self._L.effort_model_step(self._h, None if token is None else token.data_ptr(), float(effort),

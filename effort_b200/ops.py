@@ -24,6 +24,8 @@ from ._lib import EffortError, MulArgs, check
 
 KIND_FP16, KIND_Q4 = 0, 1
 NO_REPACK = 1
+SLICE_MAJOR = 2
+CUTOFF_SELECT, CUTOFF_BISECT = 0, 1
 
 
 def _stream_ptr() -> int:
@@ -62,6 +64,21 @@ class Context:
                 self._h = None
         except Exception:
             pass
+
+
+    def setCutoffMode(self, mode):
+        """'select' (default: exact order statistic, ~1 us) or 'bisect' (the reference's findCutoff32 loop bit for bit)."""
+        m = {"select": CUTOFF_SELECT, "bisect": CUTOFF_BISECT}.get(mode, mode)
+        check(self._L.effort_ctx_set_cutoff_mode(self._h, int(m)), "effort_ctx_set_cutoff_mode")
+
+    def setOption(self, name: str, value: int):
+        """A/B knobs of the fused operator: 'engine' (2|1), 'stage' (0 cp.async | 1 cp.async.bulk), 'dynamic' (1|0)."""
+        check(self._L.effort_ctx_set_option(self._h, name.encode(), int(value)), f"effort_ctx_set_option({name})")
+
+    def errorFlag(self) -> int:
+        f = C.c_uint(0)
+        check(self._L.effort_ctx_error_flag(self._h, C.byref(f), _stream_ptr()), "effort_ctx_error_flag")
+        return int(f.value)
 
 
 _default_ctx: dict[int, Context] = {}
@@ -233,6 +250,14 @@ def mul(by: ExpertWeights, out, ctx: Optional[Context] = None):
     _check_vec(out, by.outSize, "out")
     check(ctx._L.effort_mul(ctx._h, by._h, out.data_ptr(), _stream_ptr()), "mul")
     return out
+
+
+def lastCutoff(ctx: Optional[Context] = None) -> float:
+    """The cutoff the last fused operator (batch slot 0) on this context used."""
+    ctx = ctx or default_context()
+    c = C.c_float(0)
+    check(ctx._L.effort_read_dispatch(ctx._h, None, 0, None, None, C.byref(c), None, _stream_ptr()), "read")
+    return float(c.value)
 
 
 def lastSelected(ctx: Optional[Context] = None) -> int:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define EFFORT_B200_VERSION 100
+#define EFFORT_B200_VERSION 200
 
 /* error codes */
 #define EFFORT_OK 0
@@ -46,6 +46,9 @@ extern "C" {
  * slower gathers, zero extra memory).  Without it the library builds its own repacked copy and the
  * caller's buckets/stats are only needed again by the effort_calc_dispatch/effort_mul test hooks. */
 #define EFFORT_WEIGHTS_NO_REPACK 1u
+/* device copy in the slice-major layout [column slice of 128][input][rank]: the rank rows an input selects inside a
+ * column slice are contiguous, so a streaming unit is one cp.async.bulk (TMA) copy.  Round-2 engine only. */
+#define EFFORT_WEIGHTS_SLICE_MAJOR 2u
 
 #define EFFORT_PROBES_COUNT 4096 /* bucketMul.swift:19, loader.swift:66 */
 
@@ -65,6 +68,29 @@ const char* effort_last_cuda_error(void);
  * `device` = CUDA device ordinal (-1 = current). */
 int effort_ctx_create(int device, effort_ctx_t** ctx_out);
 int effort_ctx_destroy(effort_ctx_t* ctx);
+/*
+ * How calcDispatch's cutoff (findCutoff32, bucketMul.metal:141-247) is computed by the fused operator:
+ *   EFFORT_CUTOFF_SELECT (default)  the exact order statistic the reference's bisection approximates: the (k+1)-th
+ *                                   largest of the 4096 bf16 probe products, k = 4096 - Int(4095*(1-effort)), so exactly
+ *                                   k products lie above it (0 when k = 4096) -- a radix select, ~1 us;
+ *   EFFORT_CUTOFF_BISECT            the reference's loop replayed bit for bit (same fp32 result and loop count).
+ * Both satisfy the reference's own acceptance rule (count within 2 of k, bucketMul.metal:236).  effort_find_cutoff and
+ * effort_calc_dispatch (the test hooks) always run the bisection.  Environment default: EFFORT_CUTOFF=bisect.
+ */
+#define EFFORT_CUTOFF_SELECT 0
+#define EFFORT_CUTOFF_BISECT 1
+int effort_ctx_set_cutoff_mode(effort_ctx_t* ctx, int mode);
+/* Tuning / A-B knobs of the fused operator (tests and tools; every value computes the same operator):
+ *   "engine"   2 (default) round-2 kernel: one launch per group, staged streaming, reductions into `out`;
+ *              1 round-1 kernel + integrate launch (deterministic fp32 order)
+ *   "stage"    0 (default) cp.async ring, 1 cp.async.bulk (TMA) ring -- needs EFFORT_WEIGHTS_SLICE_MAJOR weights
+ *   "dynamic"  1 (default) warps take streaming units from a shared counter, 0 static round robin
+ * Returns EFFORT_EINVAL for an unknown name or value.  Environment defaults: EFFORT_ENGINE, EFFORT_STAGE=bulk,
+ * EFFORT_DYN. */
+int effort_ctx_set_option(effort_ctx_t* ctx, const char* name, int value);
+/* Non-zero once a fused kernel of this context gave up waiting for a co-resident CTA (2 s): its output is invalid.
+ * Synchronises `stream`. */
+int effort_ctx_error_flag(effort_ctx_t* ctx, unsigned* flag_out, void* stream);
 
 /* ---- weights ---------------------------------------------------------- */
 /*
@@ -235,9 +261,15 @@ const int32_t* effort_model_next_token(const effort_model_t* m);  /* device int3
 size_t effort_model_bucket_bytes(const effort_model_t* m);
 /* use CUDA graphs for effort_model_step (default 1) */
 int effort_model_set_graphs(effort_model_t* m, int enable);
-/* single-GPU FP16 only (default 1): apply rmsNorm*w on load inside the bucketMul kernels and fold the residual add
- * and silu*mul into the integrate epilogues (9 launches per layer instead of 12); 0 = one kernel per reference op */
+/* round-1 engine only (default 0): apply rmsNorm*w on load inside the round-1 bucketMul kernels and fold the residual
+ * add and silu*mul into the integrate epilogues (9 launches per layer instead of 12) */
 int effort_model_set_fused_glue(effort_model_t* m, int enable);
+/* Token chain: 2 (default; single GPU, FP16 buckets, round-2 engine) = 5 launches per layer -- [q,k,v] with
+ * rmsNorm*w applied on load, attention, wo accumulating into the residual stream, [w1,w3] with rmsNorm*w on load, w2
+ * with silu(x1)*x3 on load accumulating into the residual stream -- then one head kernel (final norm + lm_head +
+ * argmax); 1 = one kernel per reference op (runNetwork.swift:124-183 order).  Other configurations (tensor parallel,
+ * Q4, round-1 engine) always use chain 1.  Environment default: EFFORT_CHAIN. */
+int effort_model_set_chain(effort_model_t* m, int chain);
 
 /* ---- introspection used by bench / tests -------------------------------- */
 /* number of kernels this library has launched since load (process-wide) */

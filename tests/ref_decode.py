@@ -29,14 +29,18 @@ def rope(x, pos, theta=1e6, hd=128):
 class RefModel:
     """weights: list of layers, each dict name -> dict(buckets, stats, probes, in, out) + 'attn_norm','ffn_norm'."""
 
-    def __init__(self, layers, norm, out_core, emb, n_heads=32, n_kv=8, hd=128):
+    def __init__(self, layers, norm, out_core, emb, n_heads=32, n_kv=8, hd=128, fast=False):
         self.layers, self.norm, self.out_core, self.emb = layers, norm, out_core, emb
+        self.fast = fast   # the OpenMP port (fp32, chunked sum order) instead of the sequential oracle
         self.n_heads, self.n_kv, self.hd = n_heads, n_kv, hd
         self.kc = [[] for _ in layers]
         self.vc = [[] for _ in layers]
         self.pos = 0
 
     def _mul(self, v, w, effort):
+        if self.fast:
+            out, _ = O.bucket_mul_mt(v, w["buckets"], w["stats"], w["probes"], w["in"], w["out"], effort)
+            return out
         r = O.bucket_mul(v, w["buckets"], w["stats"], w["probes"], w["in"], w["out"], effort)
         return r["out32"]
 
@@ -64,6 +68,9 @@ class RefModel:
             x2 = (x3 * x1 / (1.0 + np.exp(-x1))).astype(np.float32)               # silu32b matrix.metal:25-34
             h = h + self._mul(x2, L["w2"], effort)
         on = rmsnorm_mul(h, self.norm)
-        logits, _ = O.basic_mul(on, self.out_core, cast_v=True)                    # runNetwork.swift:209
+        if self.fast:
+            logits = O.basic_mul_fast(np.float16(on).astype(np.float32), self.out_core)
+        else:
+            logits, _ = O.basic_mul(on, self.out_core, cast_v=True)                # runNetwork.swift:209
         self.pos += 1
         return logits

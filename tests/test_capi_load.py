@@ -29,7 +29,7 @@ def test_header_symbols_all_exported_and_bound():
 
 def test_version_and_strerror():
     L = _lib.load()
-    assert L.effort_version() == 100
+    assert L.effort_version() == 200
     assert L.effort_strerror(0) == b"ok"
     for code in (-1, -2, -3, -4, -5, -6):
         assert len(L.effort_strerror(code)) > 3

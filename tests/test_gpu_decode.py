@@ -33,24 +33,100 @@ def small_model():
     return m, ref
 
 
-@pytest.mark.parametrize("use_graph,fused_glue", [(False, False), (True, False), (False, True), (True, True)])
-def test_decode_matches_cpu_restatement(small_model, use_graph, fused_glue):
+@pytest.fixture(autouse=True)
+def _select_mode():
+    """the decode loop runs the operator in its default cutoff mode"""
+    with O.cutoff_mode("select"):
+        yield
+
+
+# chain 2 = the fused round-2 chain (default), chain 1 = one kernel per reference op; engine 1 = round-1 kernels
+@pytest.mark.parametrize("use_graph,chain,engine,fused_glue", [(False, 2, 2, False), (True, 2, 2, False), (True, 1, 2, False),
+                                                               (False, 1, 1, False), (True, 1, 1, True)])
+def test_decode_matches_cpu_restatement(small_model, use_graph, chain, engine, fused_glue):
     import torch
+    from effort_b200 import ops
     m, ref = small_model
-    m.set_graphs(use_graph)
-    m.set_fused_glue(fused_glue)
+    ctx = ops.default_context()
+    try:
+        ctx.setOption("engine", engine)
+        if engine == 1:
+            ctx.setCutoffMode("bisect")
+            O.set_cutoff_mode("bisect")
+        m.set_graphs(use_graph)
+        m.set_chain(chain)
+        m.set_fused_glue(fused_glue)
+        m.reset()
+        ref.pos, ref.kc, ref.vc = 0, [[] for _ in ref.layers], [[] for _ in ref.layers]
+        toks = [1, 17, 400, 999, 5]
+        for t in toks:
+            tok = torch.tensor([t], dtype=torch.int32, device="cuda")
+            m.step(tok, effort=0.5)
+            torch.cuda.synchronize()
+            got = m.logits().cpu().numpy()
+            want = ref.step(t, 0.5)
+            cs = O.cossim(got, want)
+            assert cs > 0.9995, cs     # tiny selection flips (fp32 reorder of v near the cutoff) allowed
+            assert m.next_token() == int(np.argmax(got))
+        assert ctx.errorFlag() == 0
+    finally:
+        ctx.setOption("engine", 2)
+        ctx.setCutoffMode("select")
+        m.set_chain(2)
+        m.set_fused_glue(False)
+
+
+def test_step_past_max_seq_is_refused(small_model):
+    """the KV cache holds max_seq positions: the next step is an error, not an out-of-bounds write"""
+    import torch
+    from effort_b200 import EffortError
+    m, _ = small_model
+    m.set_graphs(True)
     m.reset()
-    ref.pos, ref.kc, ref.vc = 0, [[] for _ in ref.layers], [[] for _ in ref.layers]
-    toks = [1, 17, 400, 999, 5]
-    for t in toks:
-        tok = torch.tensor([t], dtype=torch.int32, device="cuda")
-        m.step(tok, effort=0.5)
+    tok = torch.tensor([1], dtype=torch.int32, device="cuda")
+    m.step(tok, effort=0.25)
+    for _ in range(m.cfg.max_seq - 1):
+        m.step(None, effort=0.25)
+    torch.cuda.synchronize()
+    with pytest.raises(EffortError):
+        m.step(None, effort=0.25)
+    m.reset()
+    m.step(tok, effort=0.25)      # usable again after a reset
+    torch.cuda.synchronize()
+
+
+def test_32_layers_effort_025_and_long_context():
+    """BASELINE configs[1] shape: all 32 layers at effort 0.25 against the CPU restatement (OpenMP port of the oracle),
+    a few tokens; then positions >= 1024 (attention over a long KV cache) stay finite and self-consistent."""
+    import torch
+    from effort_b200.model import DecodeModel, MistralConfig
+    cfg = MistralConfig(n_layers=32, vocab=4096, max_seq=1100)
+    m = DecodeModel.random_init(cfg, seed=21, keep_reference_layout=True)
+    names = ["wq", "wk", "wv", "wo", "w1", "w2", "w3"]
+    layers = []
+    for L in m.layers:
+        d = {n: {"buckets": _cpu(ew.buckets), "stats": _cpu(ew.stats), "probes": _cpu(ew.probes), "in": ew.inSize, "out": ew.outSize}
+             for n, ew in zip(names, L[:7])}
+        d["attn_norm"], d["ffn_norm"] = _cpu(L[7]), _cpu(L[8])
+        layers.append(d)
+    ref = RefModel(layers, _cpu(m.head[0]), _cpu(m.head[1]), _cpu(m.head[2]), fast=True)
+    m.reset()
+    worst = 1.0
+    for t in (1, 77, 2049):
+        m.step(torch.tensor([t], dtype=torch.int32, device="cuda"), effort=0.25)
         torch.cuda.synchronize()
         got = m.logits().cpu().numpy()
-        want = ref.step(t, 0.5)
-        cs = O.cossim(got, want)
-        assert cs > 0.9995, cs     # tiny selection flips (fp32 reorder of v near the cutoff) allowed
-        assert m.next_token() == int(np.argmax(got))
+        want = ref.step(t, 0.25)
+        worst = min(worst, O.cossim(got, want))
+    print("32-layer effort-0.25 decode: worst logit cos-sim vs CPU restatement", worst)
+    assert worst > 0.995, worst
+    del ref, layers
+    for _ in range(1050):
+        m.step(None, effort=0.25)
+    torch.cuda.synchronize()
+    lg = m.logits().cpu().numpy()
+    assert np.isfinite(lg).all()
+    assert m.next_token() == int(np.argmax(lg))
 
 
 def test_step_host_and_self_feeding(small_model):
@@ -71,13 +147,13 @@ def test_step_host_and_self_feeding(small_model):
     for _ in range(5):
         t = m.step_host(None, effort=0.25)
         seq_b.append(t)
-    assert seq_a == seq_b                                  # deterministic generation (the reference's is not)
+    assert seq_a == seq_b                                  # same greedy continuation (argmax gaps >> fp32 reorder noise)
 
 
 def test_model_directory_roundtrip(tmp_path):
     """convert -> bucketed-safetensors directory -> load (C-ABI loader and Python reader) -> decode: the loaded models
-    reproduce the in-memory model of the same seed bit for bit (same weights, deterministic kernels); a
-    percentLoad-truncated load (loader.swift:113-166) runs and correlates."""
+    reproduce the in-memory model of the same seed (same weights); a percentLoad-truncated load
+    (loader.swift:113-166) runs and correlates."""
     import torch
     from effort_b200.model import DecodeModel, MistralConfig
     cfg = MistralConfig(n_layers=1, vocab=1024, max_seq=32)
@@ -97,9 +173,9 @@ def test_model_directory_roundtrip(tmp_path):
             torch.cuda.synchronize()
             seq.append(m.logits().cpu().numpy())
         outs[name] = seq
-    for name in ("native", "python"):
+    for name in ("native", "python"):   # same weights; the CTA sums meet in the outputs in no fixed order
         for a, b in zip(outs["mem"], outs[name]):
-            assert np.array_equal(a, b), name
+            assert O.cossim(a, b) > 0.999999, name
     # percentLoad 8 drops ranks 8..15.  On iid-Gaussian weights those ranks ARE selected at effort 0.25 (the row means
     # fall slowly with rank), so the truncated model only correlates with the full one (measured 0.86 on the first
     # token); real Mistral weights are what the reference's percentLoad knob is for (loader.swift:113-166).

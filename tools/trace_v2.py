@@ -1,0 +1,41 @@
+"""Phase timeline of bucket_mul_v2_kernel (EFFORT_TRACE=1): per-CTA globaltimer stamps of one isolated launch."""
+import argparse, ctypes as C, os, sys
+import numpy as np
+os.environ["EFFORT_TRACE"] = "1"
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from effort_b200 import ops, _lib  # noqa: E402
+from tools.sweep import rand_weights, make_v_gpu  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--shape", default="4096x14336")
+ap.add_argument("--effort", type=float, default=0.25)
+a = ap.parse_args()
+in_dim, out_dim = (int(x) for x in a.shape.split("x"))
+ws = [rand_weights(out_dim, in_dim, 100 + c)[0] for c in range(4)]
+v = make_v_gpu(in_dim)
+out = torch.empty(out_dim, dtype=torch.float32, device="cuda")
+ctx = ops.default_context()
+L = _lib.load()
+L.effort_debug_read_trace.restype = C.c_int
+L.effort_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+for k in range(200):
+    ops.bucketMul(v, ws[k % 4], None, out, a.effort)
+torch.cuda.synchronize()
+names = {0: "start", 1: "init done", 2: "v loaded", 3: "scored", 6: "cutoff", 8: "listed", 9: "streamed", 10: "reduced"}
+for rep in range(3):
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    ops.bucketMul(v, ws[rep % 4], None, out, a.effort)
+    e.record()
+    torch.cuda.synchronize()
+    buf = np.zeros((148, 16), dtype=np.uint64)
+    n = L.effort_debug_read_trace(ctx._h, buf.ctypes.data, 148)
+    t = buf[:n].astype(np.int64)
+    t = t[t[:, 0] > 0]
+    t0 = t[:, 0].min()
+    print(f"{a.shape} effort {a.effort} rep {rep}: event total {s.elapsed_time(e)*1000:.1f} us; ctas {len(t)}; selected {ops.lastSelected()}")
+    for k, nm in names.items():
+        rel = (t[:, k] - t0) / 1000.0
+        print(f"   {nm:10s} min {rel.min():7.2f}  median {np.median(rel):7.2f}  max {rel.max():7.2f} us")
