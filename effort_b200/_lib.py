@@ -73,6 +73,10 @@ SIGNATURES = {
     "effort_loader_has": (C.c_int, [vp, C.c_char_p]),
     "effort_loader_tensor": (C.c_int, [vp, C.c_char_p, vp]),
     "effort_bf16_to_f16": (C.c_int, [vp, vp, C.c_size_t]),
+    "effort_saver_open": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "effort_saver_add": (C.c_int, [vp, C.c_int, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int64), vp, C.c_size_t]),
+    "effort_saver_save": (C.c_int, [vp]),
+    "effort_saver_close": (None, [vp]),
 }
 
 

@@ -70,6 +70,7 @@ struct V2Batch {
     int n;
     int list_cap;            // units
     int dynamic;             // 1: warps take units from a shared counter; 0: static round robin
+    int ring_bytes;          // bucket_mul_v3_kernel: bytes of the producer's staging ring
     int cta_begin[kMulBatchMax + 1];
     V2Problem p[kMulBatchMax];
 };

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <new>
 #include <string>
 #include <utility>
@@ -13,6 +14,7 @@
 
 #include "bucket_mul.cuh"
 #include "bucket_mul_v2.cuh"
+#include "bucket_mul_v3.cuh"
 #include "comm.cuh"
 #include "convert.cuh"
 #include "cutoff.cuh"
@@ -82,9 +84,10 @@ struct effort_ctx {
     unsigned* v2_sync = nullptr;          // [kMaxBatch][kV2MaxSlices][2] arrive/depart counters (overwrite protocol)
     unsigned* v2_err = nullptr;           // [1] set by a kernel whose overwrite barrier timed out
     int cutoff_mode = 0;                  // EFFORT_CUTOFF_SELECT / EFFORT_CUTOFF_BISECT
-    int stage_mode = 0;                   // 0 = cp.async (LDGSTS) ring, 1 = cp.async.bulk (TMA) ring
+    int stage_mode = 2;                   // 2 = TMA pipeline (producer warp + byte ring; slice-major FP16 weights),
+                                          // 0 = per-warp cp.async (LDGSTS) rings, 1 = per-warp cp.async.bulk rings
     int engine = 2;                       // 2 = bucket_mul_v2_kernel, 1 = round-1 fused kernel + integrate
-    int dynamic = 1;                      // v2 streaming: units from a shared counter (1) or static round robin (0)
+    int dynamic = 0;                      // v2 per-warp rings: units from a shared counter (1) or static round robin (0, measured faster)
     int last_rs[8] = {0};                 // row splits of the last v2 launch per batch slot (effort_last_selected)
     bool last_was_v2 = false;
     void* comm = nullptr;                  // ncclComm_t
@@ -145,9 +148,9 @@ extern "C" int effort_ctx_create(int device, effort_ctx_t** ctx_out) {
     CK(cudaMemset(c->sel_counts, 0, sizeof(uint32_t) * kMaxBatch * c->n_sms));
     c->sel_cap = (size_t)kMaxBatch * c->n_sms;
     { const char* e = getenv("EFFORT_CUTOFF"); if (e && !strcmp(e, "bisect")) c->cutoff_mode = 1; }
-    { const char* e = getenv("EFFORT_STAGE"); if (e && !strcmp(e, "bulk")) c->stage_mode = 1; }
+    { const char* e = getenv("EFFORT_STAGE"); if (e) c->stage_mode = !strcmp(e, "bulk") ? 1 : !strcmp(e, "ldgsts") ? 0 : 2; }
     { const char* e = getenv("EFFORT_ENGINE"); if (e && atoi(e) == 1) c->engine = 1; }
-    { const char* e = getenv("EFFORT_DYN"); if (e && atoi(e) == 0) c->dynamic = 0; }
+    { const char* e = getenv("EFFORT_DYN"); if (e) c->dynamic = atoi(e) ? 1 : 0; }
     if (getenv("EFFORT_TRACE")) {
         CK(cudaMalloc(&c->trace, sizeof(unsigned long long) * 16 * c->n_sms));
         CK(cudaMemset(c->trace, 0, sizeof(unsigned long long) * 16 * c->n_sms));
@@ -165,7 +168,7 @@ extern "C" int effort_ctx_set_cutoff_mode(effort_ctx_t* c, int mode) {
 extern "C" int effort_ctx_set_option(effort_ctx_t* c, const char* name, int value) {
     if (!c || !name) return EFFORT_EINVAL;
     if (!strcmp(name, "engine")) { if (value != 1 && value != 2) return EFFORT_EINVAL; c->engine = value; return EFFORT_OK; }
-    if (!strcmp(name, "stage")) { if (value != 0 && value != 1) return EFFORT_EINVAL; c->stage_mode = value; return EFFORT_OK; }
+    if (!strcmp(name, "stage")) { if (value < 0 || value > 2) return EFFORT_EINVAL; c->stage_mode = value; return EFFORT_OK; }
     if (!strcmp(name, "dynamic")) { if (value != 0 && value != 1) return EFFORT_EINVAL; c->dynamic = value; return EFFORT_OK; }
     return EFFORT_EINVAL;
 }
@@ -270,7 +273,8 @@ extern "C" int effort_weights_create(const void* buckets_dev, const void* stats_
         w->owned += (size_t)n_experts * EFFORT_PROBES_COUNT * sizeof(__half);
         if (kind == EFFORT_KIND_FP16) {
             const bool repack = !(flags & EFFORT_WEIGHTS_NO_REPACK);
-            const bool slice_major = repack && ((flags & EFFORT_WEIGHTS_SLICE_MAJOR) || default_slice_major()) && (w->C % 8) == 0;
+            const bool slice_major = repack && !(flags & EFFORT_WEIGHTS_INPUT_MAJOR) &&
+                                     ((flags & EFFORT_WEIGHTS_SLICE_MAJOR) || default_slice_major()) && (w->C % 8) == 0;
             w->layout = repack ? (slice_major ? kSliceMajor : kInputMajor) : kRankMajor;
             CK(cudaMalloc(&w->st16, rows * sizeof(__half)));
             w->owned += rows * sizeof(__half);
@@ -321,9 +325,13 @@ static inline int effort_q(double effort, int n_probes) {
     return (int)x;
 }
 
-static bool default_slice_major() {  // EFFORT_LAYOUT=slice: device copy in the slice-major layout (v2 engine only)
+static bool default_slice_major() {  // the device copy is slice-major unless EFFORT_LAYOUT=input (round-1 engine: input-major only)
     static int v = -1;
-    if (v < 0) { const char* e = getenv("EFFORT_LAYOUT"); v = (e && !strcmp(e, "slice")) ? 1 : 0; }
+    if (v < 0) {
+        const char* e = getenv("EFFORT_LAYOUT");
+        const char* g = getenv("EFFORT_ENGINE");
+        v = ((e && !strcmp(e, "input")) || (g && atoi(g) == 1)) ? 0 : 1;
+    }
     return v == 1;
 }
 
@@ -511,28 +519,41 @@ static int launch_v2_batch(effort_ctx* ctx, const V2Call* calls, int n, int slot
     batch.cta_begin[n] = cta;
     batch.list_cap = (list_cap + 63) & ~63;
     using L = V2Smem<SLOTS, VEC>;
-    bool bulk = ctx->stage_mode == 1;
+    bool bulk = ctx->stage_mode == 1;  // per-warp bulk rings (experiment)
     // one bulk copy per unit needs the unit's rows contiguous in HBM: the slice-major device layout
     for (int k = 0; k < n; k++) bulk = bulk && calls[k].w->layout == kSliceMajor;
     batch.dynamic = ctx->dynamic;
     const size_t smem = L::bytes(batch.list_cap, D);
     if (smem > kMaxSmem) return EFFORT_ESHAPE;
-    auto go = [&](auto kernel) -> int {
-        static bool configured[64] = {false};  // per kernel instantiation and device
-        const int dev = ctx->device & 63;
-        if (!configured[dev]) {
+    // every kernel needs its own opt-in to > 48 KB of dynamic shared memory (per device): keyed by the function pointer
+    // (all instantiations share ONE pointer type, so a static inside a generic lambda would be shared between them)
+    auto go = [&](void (*kernel)(const V2Batch), int threads, size_t smem_bytes) -> int {
+        static std::map<std::pair<int, const void*>, bool> configured;
+        const auto key = std::make_pair(ctx->device, (const void*)kernel);
+        if (!configured.count(key)) {
             CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-            configured[dev] = true;
+            configured[key] = true;
         }
-        CK(launch_pdl(kernel, dim3(cta), dim3(kV2Threads), smem, stream, batch));
+        CK(launch_pdl(kernel, dim3(cta), dim3(threads), smem_bytes, stream, batch));
         return EFFORT_OK;
     };
     int rc;
     const bool bisect = ctx->cutoff_mode == 1;
-    if (bisect) rc = bulk ? go(bucket_mul_v2_kernel<SLOTS, VEC, kCutBisect, kStageBulk, D>)
-                          : go(bucket_mul_v2_kernel<SLOTS, VEC, kCutBisect, kStageLdgsts, D>);
-    else rc = bulk ? go(bucket_mul_v2_kernel<SLOTS, VEC, kCutSelect, kStageBulk, D>)
-                   : go(bucket_mul_v2_kernel<SLOTS, VEC, kCutSelect, kStageLdgsts, D>);
+    bool all_slice = true;
+    for (int k = 0; k < n; k++) all_slice = all_slice && calls[k].w->layout == kSliceMajor;
+    if (SLOTS == 16 && all_slice && ctx->stage_mode == 2) {
+        // TMA pipeline: producer warp + byte ring (bucket_mul_v3.cuh)
+        batch.ring_bytes = (int)((kMaxSmem - V3Smem::kFixed) & ~(size_t)255);
+        if (batch.ring_bytes < 2 * (kV3BatchBytes + 4096)) return EFFORT_ESHAPE;
+        const size_t smem3 = V3Smem::kFixed + (size_t)batch.ring_bytes;
+        rc = bisect ? go(bucket_mul_v3_kernel<kCutBisect>, kV3Threads, smem3) : go(bucket_mul_v3_kernel<kCutSelect>, kV3Threads, smem3);
+    } else if (bisect) {
+        rc = bulk ? go(bucket_mul_v2_kernel<SLOTS, VEC, kCutBisect, kStageBulk, D>, kV2Threads, smem)
+                  : go(bucket_mul_v2_kernel<SLOTS, VEC, kCutBisect, kStageLdgsts, D>, kV2Threads, smem);
+    } else {
+        rc = bulk ? go(bucket_mul_v2_kernel<SLOTS, VEC, kCutSelect, kStageBulk, D>, kV2Threads, smem)
+                  : go(bucket_mul_v2_kernel<SLOTS, VEC, kCutSelect, kStageLdgsts, D>, kV2Threads, smem);
+    }
     if (rc) return rc;
     LAUNCHED();
     ctx->last_was_v2 = true;
@@ -599,6 +620,7 @@ static int enqueue_bucket_mul(effort_ctx* ctx, const float* v, const effort_weig
         return launch_v2(ctx, &c, 1, slot, stream);
     }
     ctx->last_was_v2 = false;
+    if (w->layout == kSliceMajor) return EFFORT_ESHAPE;  // the round-1 kernels read input-major / rank-major rows only
     int rc = ensure_mul_scratch(ctx, 0, kMaxBatch);
     if (rc) return rc;
     MulCall c = make_call(ctx, v, w, exp_no, out, effort, accumulate, slot, partial_off);
@@ -736,6 +758,7 @@ extern "C" int effort_expert_mul_batch(effort_ctx_t* ctx, const effort_mul_args_
     for (int k = 0; k < n; k++) {
         const effort_weights* w = args[k].w;
         if (w->kind == EFFORT_KIND_FP16 && w->buckets) {
+            if (w->layout == kSliceMajor) return EFFORT_ESHAPE;
             if (ng == kMulBatchMax && (rc = flush())) return rc;
             group[ng++] = make_call(ctx, args[k].v_dev, w, args[k].exp_no_dev, args[k].out_dev, args[k].effort, 0, k, off,
                                     args[k].v_cutoff_dev);

@@ -11,6 +11,7 @@
 // pointers can be handed straight to cudaMemcpy (or wrapped by numpy) without another copy.
 // No CUDA in this file: it is the "loader" row of SURVEY.md section 8(f), and it is unit-tested on the CPU.
 #include <fcntl.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <string.h>
 #include <sys/mman.h>
@@ -19,6 +20,7 @@
 
 #include <map>
 #include <memory>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -96,6 +98,7 @@ struct JParser {
                             p += 2;
                             unsigned lo;
                             if (!hex4(lo)) return false;
+                            if (lo < 0xDC00 || lo >= 0xE000) return false;  // not a low surrogate
                             cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
                         }
                         utf8(out, cp);
@@ -230,13 +233,15 @@ int open_file(const std::string& path, std::unique_ptr<StFile>& out) {
         uint64_t count = 1;
         const double kMaxExact = 9007199254740992.0;  // 2^53: beyond it a JSON number is not an exact integer
         for (auto& d : sh->arr) {
-            if (d.kind != JVal::kNum || !(d.num >= 0) || d.num > kMaxExact) return EFFORT_EINVAL;
+            if (d.kind != JVal::kNum || !(d.num >= 0) || d.num > kMaxExact || d.num != (double)(uint64_t)d.num) return EFFORT_EINVAL;
             r.shape.push_back((int64_t)d.num);
             if (d.num != 0 && count > (uint64_t)kMaxExact / (uint64_t)d.num) return EFFORT_EINVAL;  // overflow
             count *= (uint64_t)d.num;
         }
         for (int k = 0; k < 2; k++)
-            if (off->arr[k].kind != JVal::kNum || !(off->arr[k].num >= 0) || off->arr[k].num > kMaxExact) return EFFORT_EINVAL;
+            if (off->arr[k].kind != JVal::kNum || !(off->arr[k].num >= 0) || off->arr[k].num > kMaxExact ||
+                off->arr[k].num != (double)(uint64_t)off->arr[k].num)
+                return EFFORT_EINVAL;
         r.begin = (uint64_t)off->arr[0].num;
         r.end = (uint64_t)off->arr[1].num;
         if (r.end < r.begin || r.end > f->size - f->data_off) return EFFORT_EINVAL;
@@ -371,4 +376,137 @@ extern "C" int effort_bf16_to_f16(const uint16_t* src, uint16_t* dst, size_t n) 
         dst[i] = h;
     }
     return EFFORT_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// writer: TensorSaver (helpers/safetensors.swift:38-85) + saveSafetensors (:222-280)
+// ---------------------------------------------------------------------------------------------------------------
+// files[i] collects named host tensors; save() writes "<model>-%05d-of-%05d.safetensors" (u64 little-endian header
+// size, JSON header {name: {"dtype", "shape", "data_offsets"}, "__metadata__": {"description": ...}}, tensor bytes in
+// header order) and "<model>.safetensors.index.json" {"weight_map": {name: file}}.  The saver copies nothing: the
+// caller's buffers must stay valid until effort_saver_save returns.
+namespace {
+struct SaveRec {
+    std::string name;
+    int dtype;
+    std::vector<int64_t> shape;
+    const void* data;
+    size_t nbytes;
+};
+void json_escape(std::string& o, const std::string& s) {
+    o += '"';
+    for (unsigned char c : s) {
+        switch (c) {
+            case '"': o += "\\\""; break;
+            case '\\': o += "\\\\"; break;
+            case '\n': o += "\\n"; break;
+            case '\r': o += "\\r"; break;
+            case '\t': o += "\\t"; break;
+            default:
+                if (c < 0x20) { char b[8]; snprintf(b, sizeof(b), "\\u%04x", c); o += b; }
+                else o += (char)c;
+        }
+    }
+    o += '"';
+}
+const char* dtype_name(int code) { return code == EFFORT_ST_F16 ? "F16" : code == EFFORT_ST_BF16 ? "BF16" : "F32"; }
+bool write_all(int fd, const void* buf, size_t n) {
+    const char* p = (const char*)buf;
+    while (n) {
+        ssize_t w = write(fd, p, n > ((size_t)1 << 30) ? ((size_t)1 << 30) : n);
+        if (w <= 0) return false;
+        p += w;
+        n -= (size_t)w;
+    }
+    return true;
+}
+}  // namespace
+
+struct effort_saver {
+    std::string dir, model, description;
+    std::vector<std::vector<SaveRec>> files;
+};
+
+extern "C" int effort_saver_open(const char* dir, const char* model, const char* description, effort_saver_t** out) {
+    if (!dir || !model || !out) return EFFORT_EINVAL;
+    effort_saver* s = new (std::nothrow) effort_saver();
+    if (!s) return EFFORT_ENOMEM;
+    s->dir = dir;
+    s->model = model;
+    s->description = description ? description : "Bucket weights format, see mixtral-kolinko at github";  // safetensors.swift:249
+    *out = s;
+    return EFFORT_OK;
+}
+
+extern "C" void effort_saver_close(effort_saver_t* s) { delete s; }
+
+extern "C" int effort_saver_add(effort_saver_t* s, int file_index, const char* name, int dtype, int ndim,
+                                const int64_t* shape, const void* data_host, size_t nbytes) {
+    if (!s || !name || file_index < 0 || file_index > 100000 || ndim < 0 || ndim > EFFORT_ST_MAX_DIMS || (ndim && !shape) ||
+        (nbytes && !data_host))
+        return EFFORT_EINVAL;
+    if (dtype != EFFORT_ST_F16 && dtype != EFFORT_ST_F32 && dtype != EFFORT_ST_BF16) return EFFORT_EINVAL;  // :231-247
+    uint64_t count = 1;
+    for (int d = 0; d < ndim; d++) {
+        if (shape[d] < 0) return EFFORT_EINVAL;
+        count *= (uint64_t)shape[d];
+    }
+    if (count * (uint64_t)dtype_size(dtype) != (uint64_t)nbytes) return EFFORT_ESHAPE;
+    while ((int)s->files.size() <= file_index) s->files.emplace_back();  // subscript setter, :49-61
+    for (auto& f : s->files)
+        for (auto& r : f)
+            if (r.name == name) return EFFORT_ESTATE;  // a tensor name maps to ONE file in the index
+    SaveRec r;
+    r.name = name; r.dtype = dtype; r.shape.assign(shape, shape + ndim); r.data = data_host; r.nbytes = nbytes;
+    s->files[(size_t)file_index].push_back(std::move(r));
+    return EFFORT_OK;
+}
+
+extern "C" int effort_saver_save(effort_saver_t* s) {
+    if (!s) return EFFORT_EINVAL;
+    mkdir(s->dir.c_str(), 0777);
+    std::string index = "{\n  \"weight_map\": {";
+    bool first = true;
+    char fname[256];
+    for (size_t id = 0; id < s->files.size(); id++) {
+        snprintf(fname, sizeof(fname), "%s-%05d-of-%05d.safetensors", s->model.c_str(), (int)id + 1, (int)s->files.size());  // :67
+        std::string hdr = "{";
+        uint64_t off = 0;
+        for (auto& r : s->files[id]) {
+            json_escape(hdr, r.name);
+            hdr += ":{\"dtype\":\"";
+            hdr += dtype_name(r.dtype);
+            hdr += "\",\"shape\":[";
+            for (size_t d = 0; d < r.shape.size(); d++) { if (d) hdr += ','; hdr += std::to_string(r.shape[d]); }
+            hdr += "],\"data_offsets\":[" + std::to_string(off) + "," + std::to_string(off + r.nbytes) + "]},";
+            off += r.nbytes;
+            index += first ? "\n    " : ",\n    ";
+            first = false;
+            json_escape(index, r.name);
+            index += ": ";
+            json_escape(index, fname);
+        }
+        hdr += "\"__metadata__\":{\"description\":";
+        json_escape(hdr, s->description);
+        hdr += "}}";
+        while (hdr.size() % 8) hdr += ' ';  // keep the tensor bytes 8-byte aligned (allowed padding of the header)
+        const std::string path = join_path(s->dir, fname);
+        int fd = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+        if (fd < 0) return EFFORT_EINVAL;
+        uint64_t n = hdr.size();
+        unsigned char le[8];
+        for (int b = 0; b < 8; b++) le[b] = (unsigned char)(n >> (8 * b));
+        bool ok = write_all(fd, le, 8) && write_all(fd, hdr.data(), hdr.size());
+        for (auto& r : s->files[id]) ok = ok && write_all(fd, r.data, r.nbytes);
+        ok = (close(fd) == 0) && ok;
+        if (!ok) return EFFORT_EINVAL;
+    }
+    index += "\n  }\n}\n";
+    const std::string ipath = join_path(s->dir, s->model + ".safetensors.index.json");
+    int fd = open(ipath.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    if (fd < 0) return EFFORT_EINVAL;
+    bool ok = write_all(fd, index.data(), index.size());
+    ok = (close(fd) == 0) && ok;
+    return ok ? EFFORT_OK : EFFORT_EINVAL;
 }

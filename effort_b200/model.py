@@ -111,7 +111,7 @@ class DecodeModel:
     @classmethod
     def random_init(cls, cfg: MistralConfig = MistralConfig(), seed: int = 1234, keep_reference_layout: bool = False,
                     ctx: Optional[ops.Context] = None, norm_jitter: float = 0.1, tp_rank: int = 0,
-                    tp_size: int = 1) -> "DecodeModel":
+                    tp_size: int = 1, weight_flags: int = 0, weight_fn=None) -> "DecodeModel":
         """Random-init weights ~ N(0, 0.02^2), converted on the GPU (effort_bucketize).
         With tp_size > 1 every rank draws the SAME full matrices (same seed), converts them and keeps its shard
         (effort_b200/sharding.py): the sharded model computes what the unsharded one does."""
@@ -120,13 +120,13 @@ class DecodeModel:
         kvd = cfg.n_kv_heads * cfg.head_dim
 
         def make(out_dim, in_dim, mode="column"):
-            w = _rand_w(out_dim, in_dim, gen)
+            w = (weight_fn or _rand_w)(out_dim, in_dim, gen)
             t = ops.bucketize(w)
             if tp_size > 1:
                 fn = sharding.shard_columns if mode == "column" else sharding.shard_rows
                 t = fn(t, in_dim, out_dim, tp_rank, tp_size)
                 in_dim, out_dim = t["in"], t["out"]
-            ew = ops.ExpertWeights(t["buckets"], t["bucket.stats"], t["probes"], inDim=in_dim, outDim=out_dim)
+            ew = ops.ExpertWeights(t["buckets"], t["bucket.stats"], t["probes"], inDim=in_dim, outDim=out_dim, flags=weight_flags)
             if not keep_reference_layout:
                 ew.release_reference_layout()
             return ew
@@ -147,38 +147,121 @@ class DecodeModel:
         torch.cuda.empty_cache()
         return m
 
-    # -- model directory (the reference's on-disk contract, weights_io.py) ------------------------------------
-    @staticmethod
-    def convert_random_to_directory(path: str, cfg: MistralConfig = MistralConfig(), seed: int = 1234,
-                                    norm_jitter: float = 0.1) -> str:
-        """convertMistral (convert.swift:59-127) on random-init weights: bucketize every projection on the GPU and
-        write one bucketed-safetensors file per layer + the index.  Draws the SAME random sequence as random_init
-        (same seed => same model), so a loaded model can be compared with the in-memory one bit for bit."""
-        from . import weights_io
+    @classmethod
+    def random_init_q4(cls, cfg: MistralConfig = MistralConfig(), seed: int = 1234, ctx: Optional[ops.Context] = None,
+                       norm_jitter: float = 0.1, bucketed=("wq", "w1", "w2", "w3"), keep_tensors: bool = False) -> "DecodeModel":
+        """BASELINE configs[2]: a Q4 model.  The reference's converter bucketizes only wq / w1 / w2 / w3
+        (q4_convert.py:53,59: 2 % outliers kept as fp32 records, the rest as sign|position nibbles in size-8 buckets,
+        q4_draft.py:70-322); wk / wv / wo stay dense fp16 `core` tensors and expertMul routes them to basicMul
+        (expertMul.swift:26-31).  keep_tensors=True leaves the converted tensors on the ExpertWeights objects
+        (`q4_tensors`, `dense`) for the CPU restatement in tests."""
+        from . import convert
+        m = cls(cfg, ctx)
         gen = torch.Generator(device="cuda").manual_seed(seed)
         kvd = cfg.n_kv_heads * cfg.head_dim
-        files = []
+
+        def make(name, out_dim, in_dim):
+            w = _rand_w(out_dim, in_dim, gen)
+            if name in bucketed:
+                t = convert.q4_convert(w.t().contiguous())          # W^T [in, out], as q4_convert.py:53 passes it
+                ew = ops.ExpertWeights(t["buckets"], t["bucket.stats"], t["probes"], t["outliers"], None, inDim=in_dim,
+                                       outDim=out_dim, kind=ops.KIND_Q4)
+                if keep_tensors:
+                    ew.q4_tensors = t
+            else:
+                ew = ops.ExpertWeights(core=w, inDim=in_dim, outDim=out_dim, kind=ops.KIND_Q4)
+            if keep_tensors:
+                ew.dense = w
+            return ew
 
         def norm_vec():
             return (1.0 + norm_jitter * torch.randn(cfg.dim, generator=gen, device="cuda")).half()
 
         for i in range(cfg.n_layers):
-            names = weights_io.layer_tensor_names(i)
-            t = {}
-            for key, (o, n) in (("wq", (cfg.dim, cfg.dim)), ("wk", (kvd, cfg.dim)), ("wv", (kvd, cfg.dim)), ("wo", (cfg.dim, cfg.dim)),
-                                ("w1", (cfg.hidden_dim, cfg.dim)), ("w2", (cfg.dim, cfg.hidden_dim)), ("w3", (cfg.hidden_dim, cfg.dim))):
-                conv = ops.bucketize(_rand_w(o, n, gen))
-                torch.cuda.synchronize()
-                for part in ("buckets", "bucket.stats", "probes"):
-                    t[names[key] + part] = conv[part].cpu().numpy()
-            t[f"layers.{i}.attention_norm"] = norm_vec().cpu().numpy()
-            t[f"layers.{i}.ffn_norm"] = norm_vec().cpu().numpy()
-            files.append(t)
-        out_core = _rand_w(cfg.vocab, cfg.dim, gen)
-        files[0]["model.norm"] = norm_vec().cpu().numpy()                      # convert.swift:70-74: with layer 0
-        files[0]["output.core"] = out_core.cpu().numpy()
-        files[0]["tok_embeddings.core"] = _rand_w(cfg.vocab, cfg.dim, gen, scale=1.0).cpu().numpy()
-        return weights_io.save_model(path, files)
+            m.set_layer(i, make("wq", cfg.dim, cfg.dim), make("wk", kvd, cfg.dim), make("wv", kvd, cfg.dim),
+                        make("wo", cfg.dim, cfg.dim), make("w1", cfg.hidden_dim, cfg.dim), make("w2", cfg.dim, cfg.hidden_dim),
+                        make("w3", cfg.hidden_dim, cfg.dim), norm_vec(), norm_vec())
+        m.set_head(norm_vec(), _rand_w(cfg.vocab, cfg.dim, gen), _rand_w(cfg.vocab, cfg.dim, gen, scale=1.0))
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        return m
+
+    # -- model directory (the reference's on-disk contract, weights_io.py) ------------------------------------
+    @staticmethod
+    def random_hf_source(cfg: MistralConfig = MistralConfig(), seed: int = 1234, norm_jitter: float = 0.1):
+        """A random-init Mistral checkpoint under the HF tensor names convertMistral reads (convert.swift:59-106), one
+        layer at a time.  Draws the SAME random sequence as random_init (same seed => same model), so a converted +
+        loaded model can be compared with the in-memory one."""
+        from . import weights_io
+        gen = torch.Generator(device="cuda").manual_seed(seed)
+        kvd = cfg.n_kv_heads * cfg.head_dim
+        cache = {}
+        state = {"layer": -1}
+
+        def norm_vec():
+            return (1.0 + norm_jitter * torch.randn(cfg.dim, generator=gen, device="cuda")).half()
+
+        def gen_layer(i):   # random_init's order: wq wk wv wo w1 w2 w3, attention_norm, ffn_norm
+            assert i == state["layer"] + 1, "layers must be requested in order"
+            cache.clear()
+            p = f"model.layers.{i}."
+            for key, (o, n) in (("wq", (cfg.dim, cfg.dim)), ("wk", (kvd, cfg.dim)), ("wv", (kvd, cfg.dim)), ("wo", (cfg.dim, cfg.dim))):
+                cache[p + weights_io.HF_ATTN[key]] = _rand_w(o, n, gen)
+            for key, (o, n) in (("w1", (cfg.hidden_dim, cfg.dim)), ("w2", (cfg.dim, cfg.hidden_dim)), ("w3", (cfg.hidden_dim, cfg.dim))):
+                cache[p + weights_io.HF_MLP[key]] = _rand_w(o, n, gen)
+            cache[p + "input_layernorm.weight"] = norm_vec()
+            cache[p + "post_attention_layernorm.weight"] = norm_vec()
+            state["layer"] = i
+
+        head = {}
+
+        def source(name: str):
+            if name in weights_io.HF_HEAD.values():
+                if not head:   # drawn after the last layer in random_init: generate every layer's draws first
+                    raise KeyError("head tensors are produced by finish()")
+                return head[name].cpu().numpy()
+            i = int(name.split(".")[2])
+            if i != state["layer"]:
+                gen_layer(i)
+            return cache[name].cpu().numpy()
+
+        def finish():
+            out_core = _rand_w(cfg.vocab, cfg.dim, gen)
+            head["model.norm.weight"] = norm_vec()
+            head["lm_head.weight"] = out_core
+            head["model.embed_tokens.weight"] = _rand_w(cfg.vocab, cfg.dim, gen, scale=1.0)
+
+        source.finish = finish
+        return source
+
+    @staticmethod
+    def convert_random_to_directory(path: str, cfg: MistralConfig = MistralConfig(), seed: int = 1234,
+                                    norm_jitter: float = 0.1, native: bool = True) -> str:
+        """convertMistral (convert.swift:59-127) on a random-init HF-named checkpoint: bucketize every projection on the
+        GPU and write one bucketed-safetensors file per layer + the index (through the C-ABI saver, or the Python
+        safetensors package with native=False)."""
+        from . import weights_io
+        src = DecodeModel.random_hf_source(cfg, seed, norm_jitter)
+        # the head tensors live in layer 0's file but are drawn last: materialise all layers' tensors lazily through a
+        # two-pass source (layer tensors cached per layer on the host)
+        layers = {}
+        for i in range(cfg.n_layers):
+            names = [f"model.layers.{i}." + n for n in list(weights_io.HF_ATTN.values()) + list(weights_io.HF_MLP.values()) +
+                     list(weights_io.HF_NORMS.values())]
+            layers[i] = {n: src(n) for n in names}
+        src.finish()
+
+        def source(name):
+            if name in weights_io.HF_HEAD.values():
+                return src(name)
+            return layers[int(name.split(".")[2])][name]
+
+        def bucketize(w):
+            t = ops.bucketize(torch.from_numpy(w).cuda())
+            torch.cuda.synchronize()
+            return {k: v.cpu().numpy() for k, v in t.items()}
+
+        return weights_io.convert_mistral(source, path, cfg.n_layers, bucketize, native=native)
 
     @classmethod
     def from_directory(cls, path: str, cfg: MistralConfig = MistralConfig(), percent_load: int = 16, native: bool = True,

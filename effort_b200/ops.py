@@ -25,6 +25,7 @@ from ._lib import EffortError, MulArgs, check
 KIND_FP16, KIND_Q4 = 0, 1
 NO_REPACK = 1
 SLICE_MAJOR = 2
+INPUT_MAJOR = 4
 CUTOFF_SELECT, CUTOFF_BISECT = 0, 1
 
 

@@ -30,6 +30,112 @@ def layer_tensor_names(layer: int) -> Dict[str, str]:
     return names
 
 
+# HF checkpoint names -> the reference's names (convertMistral, convert.swift:59-127)
+HF_HEAD = {"model.norm": "model.norm.weight", "output.core": "lm_head.weight", "tok_embeddings.core": "model.embed_tokens.weight"}
+HF_ATTN = {"wq": "self_attn.q_proj.weight", "wk": "self_attn.k_proj.weight", "wv": "self_attn.v_proj.weight",
+           "wo": "self_attn.o_proj.weight"}
+HF_MLP = {"w1": "mlp.gate_proj.weight", "w2": "mlp.down_proj.weight", "w3": "mlp.up_proj.weight"}   # convert.swift:98-104
+HF_NORMS = {"attention_norm": "input_layernorm.weight", "ffn_norm": "post_attention_layernorm.weight"}
+
+
+def reference_loader_names(n_layers: int, n_experts: int = 1):
+    """The tensor names the reference's loader reads for a non-quantised model: (required, optional).
+    Model.init (loader.swift:254-272), Layer.init (:201-225), ExpertWeights(elName:) for attention (:60-110: `.core` is
+    read unconditionally, buckets only if `.probes` exists) and ExpertWeights(prefix, wId, ...) for the MLP (:113-166)."""
+    req = {"model.norm", "output.core", "tok_embeddings.core"}
+    opt = set()
+    for n in range(n_layers):
+        req |= {f"layers.{n}.ffn_norm", f"layers.{n}.attention_norm"}
+        if n_experts > 1:
+            req.add(f"layers.{n}.feed_forward.gate")
+        for s_ in "okqv":
+            el = f"layers.{n}.attention.w{s_}"
+            req.add(el + ".core")
+            opt |= {el + ".outliers", el + ".probes", el + ".buckets", el + ".bucket.stats"}
+        for e in range(n_experts):
+            for wid in ("w1", "w3", "w2"):
+                f = f"layers.{n}.feed_forward.experts.{e}.{wid}."
+                req |= {f + "probes", f + "buckets", f + "bucket.stats"}
+                opt |= {f + "core"} | ({f + "outliers"} if e == 0 else set())
+    return req, opt
+
+
+def convert_mistral(source, path: str, n_layers: int, bucketize, model: str = MODEL_FP16, native: bool = True) -> str:
+    """convertMistral (convert.swift:59-127): HF-named tensors in, the reference's bucketed model directory out.
+    source: callable HF tensor name -> numpy float16 array ([out, in] for matrices); bucketize: [out,in] fp16 array ->
+    {"buckets", "bucket.stats", "probes"} numpy arrays (the library's effort_bucketize on the GPU).  One file per layer;
+    layer 0 also carries model.norm / output.core / tok_embeddings.core (:70-74); every attention projection keeps its
+    dense `.core` next to the buckets (:91 -- the reference's attention loader requires it, loader.swift:60-63)."""
+    saver = (NativeTensorSaver if native else PythonTensorSaver)(path, model)
+    for n in range(n_layers):
+        t = {}
+        if n == 0:
+            for new, old in HF_HEAD.items():
+                t[new] = source(old)
+        for new, old in HF_NORMS.items():
+            t[f"layers.{n}.{new}"] = source(f"model.layers.{n}.{old}")
+        for s_ in ("k", "o", "q", "v"):                                        # the reference's order, :86
+            w = source(f"model.layers.{n}." + HF_ATTN["w" + s_])
+            pref = f"layers.{n}.attention.w{s_}."
+            for k, a in bucketize(w).items():
+                t[pref + k] = a
+            t[pref + "core"] = w
+        for wid in ("w1", "w2", "w3"):
+            w = source(f"model.layers.{n}." + HF_MLP[wid])
+            pref = f"layers.{n}.feed_forward.experts.0.{wid}."
+            for k, a in bucketize(w).items():
+                t[pref + k] = a
+        saver.add_file(n, t)
+    return saver.save()
+
+
+class PythonTensorSaver:
+    """TensorSaver through the Python safetensors package (kept as the independent implementation for tests)."""
+
+    def __init__(self, path: str, model: str = MODEL_FP16):
+        self.path, self.model, self.files = path, model, {}
+
+    def add_file(self, idx: int, tensors: dict):
+        self.files[idx] = tensors
+
+    def save(self) -> str:
+        return save_model(self.path, [self.files[i] for i in range(len(self.files))], self.model,
+                          "Bucket weights format, see mixtral-kolinko at github")
+
+
+class NativeTensorSaver:
+    """TensorSaver over the library's C-ABI writer (effort_saver_*, csrc/safetensors_io.cpp).  Files are written as
+    soon as a layer is complete would need the file count up front (it is part of the file name,
+    safetensors.swift:67), so like the reference the saver collects everything and writes in save()."""
+
+    def __init__(self, path: str, model: str = MODEL_FP16):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib, self._L = C, _lib, _lib.load()
+        self.path, self.model = path, model
+        h = C.c_void_p()
+        _lib.check(self._L.effort_saver_open(path.encode(), model.encode(), None, C.byref(h)), "effort_saver_open")
+        self._h, self._keep = h, []
+
+    _CODE = {np.dtype(np.float16): 0, np.dtype(np.float32): 2}
+
+    def add_file(self, idx: int, tensors: dict):
+        for name, a in tensors.items():
+            a = np.ascontiguousarray(a)
+            if a.dtype not in self._CODE:
+                raise TypeError(f"{name}: only float16 / float32 tensors can be saved (safetensors.swift:231-247), got {a.dtype}")
+            self._keep.append(a)   # the saver does not copy
+            shape = (self._C.c_int64 * max(1, a.ndim))(*a.shape)
+            self._lib.check(self._L.effort_saver_add(self._h, idx, name.encode(), self._CODE[a.dtype], a.ndim, shape,
+                                                     a.ctypes.data, a.nbytes), f"effort_saver_add({name})")
+
+    def save(self) -> str:
+        self._lib.check(self._L.effort_saver_save(self._h), "effort_saver_save")
+        self._L.effort_saver_close(self._h)
+        self._h, self._keep = None, []
+        return os.path.join(self.path, f"{self.model}.safetensors.index.json")
+
+
 def file_name(model: str, idx: int, count: int) -> str:
     return f"{model}-{idx + 1:05d}-of-{count:05d}.safetensors"  # safetensors.swift:67
 

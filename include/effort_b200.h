@@ -47,8 +47,11 @@ extern "C" {
  * caller's buckets/stats are only needed again by the effort_calc_dispatch/effort_mul test hooks. */
 #define EFFORT_WEIGHTS_NO_REPACK 1u
 /* device copy in the slice-major layout [column slice of 128][input][rank]: the rank rows an input selects inside a
- * column slice are contiguous, so a streaming unit is one cp.async.bulk (TMA) copy.  Round-2 engine only. */
+ * column slice are contiguous, so a streaming unit is one cp.async.bulk (TMA) copy.  Round-2 engine only; the default
+ * for FP16 weights (EFFORT_LAYOUT=input or EFFORT_ENGINE=1 in the environment makes input-major the default). */
 #define EFFORT_WEIGHTS_SLICE_MAJOR 2u
+/* device copy input-major ([input][rank][all columns]) even when slice-major is the default: what the round-1 engine reads */
+#define EFFORT_WEIGHTS_INPUT_MAJOR 4u
 
 #define EFFORT_PROBES_COUNT 4096 /* bucketMul.swift:19, loader.swift:66 */
 
@@ -83,8 +86,10 @@ int effort_ctx_set_cutoff_mode(effort_ctx_t* ctx, int mode);
 /* Tuning / A-B knobs of the fused operator (tests and tools; every value computes the same operator):
  *   "engine"   2 (default) round-2 kernel: one launch per group, staged streaming, reductions into `out`;
  *              1 round-1 kernel + integrate launch (deterministic fp32 order)
- *   "stage"    0 (default) cp.async ring, 1 cp.async.bulk (TMA) ring -- needs EFFORT_WEIGHTS_SLICE_MAJOR weights
- *   "dynamic"  1 (default) warps take streaming units from a shared counter, 0 static round robin
+ *   "stage"    2 (default) TMA pipeline: a producer warp issues one cp.async.bulk per streaming unit into a shared byte
+ *              ring, 16 consumer warps accumulate (slice-major FP16 weights; other weights take stage 0);
+ *              0 per-warp cp.async rings; 1 per-warp cp.async.bulk rings (slice-major weights)
+ *   "dynamic"  per-warp rings (stage 0/1) only: 0 (default) static round robin of the units, 1 units from a shared counter
  * Returns EFFORT_EINVAL for an unknown name or value.  Environment defaults: EFFORT_ENGINE, EFFORT_STAGE=bulk,
  * EFFORT_DYN. */
 int effort_ctx_set_option(effort_ctx_t* ctx, const char* name, int value);
@@ -305,6 +310,20 @@ int effort_loader_has(const effort_loader_t* loader, const char* name);         
 int effort_loader_tensor(effort_loader_t* loader, const char* name, effort_tensor_info_t* info);  /* fetchTensor :136-216 */
 /* convertBF16 (the reference converts BF16 tensors to fp16 after loading, safetensors.swift:207-210) */
 int effort_bf16_to_f16(const uint16_t* src, uint16_t* dst, size_t n);
+
+/* Replaces TensorSaver (helpers/safetensors.swift:38-85) + saveSafetensors (:222-280): tensors are collected per output
+ * file (the reference writes one file per layer, convert.swift:68,121) and effort_saver_save writes
+ * "<model>-%05d-of-%05d.safetensors" files (u64 LE header size, JSON header with dtype / shape / data_offsets per tensor and
+ * "__metadata__": {"description"}, tensor bytes in header order) plus "<model>.safetensors.index.json"
+ * {"weight_map": {name: file}}.  Only F16 / F32 (and BF16 pass-through) tensors, as in the reference (:231-247).  The saver
+ * does not copy: `data_host` must stay valid until effort_saver_save returns.  A name may be added once (EFFORT_ESTATE). */
+typedef struct effort_saver effort_saver_t;
+int effort_saver_open(const char* dir, const char* model, const char* description /* NULL = the reference's text */,
+                      effort_saver_t** out);
+int effort_saver_add(effort_saver_t* saver, int file_index, const char* name, int dtype, int ndim, const int64_t* shape,
+                     const void* data_host, size_t nbytes);
+int effort_saver_save(effort_saver_t* saver);
+void effort_saver_close(effort_saver_t* saver);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,13 @@ class RefModel:
         self.pos = 0
 
     def _mul(self, v, w, effort):
+        # expertMul routing (expertMul.swift:20-38): Q4 with buckets -> zero + bucketMulQ4 + outliers; Q4 without ->
+        # dense basicMul on `core`; FP16 -> bucketMul
+        kind = w.get("kind", "fp16")
+        if kind == "q4":
+            return O.bucket_mul_q4(v, w["buckets"], w["stats"], w["probes"], w["outliers"], w["in"], w["out"], effort)["out32"]
+        if kind == "core":
+            return O.basic_mul(v, w["core"], cast_v=True)[0]
         if self.fast:
             out, _ = O.bucket_mul_mt(v, w["buckets"], w["stats"], w["probes"], w["in"], w["out"], effort)
             return out

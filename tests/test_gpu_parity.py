@@ -256,14 +256,15 @@ def test_no_repack_layout_same_selection_and_sum(T, ops):
 
 
 @pytest.mark.parametrize("in_dim,out_dim", [(4096, 4096), (4096, 1024), (4096, 11008), (14336, 4096)])
-@pytest.mark.parametrize("stage", [0, 1])
-def test_slice_major_layout_and_bulk_stage(T, ops, in_dim, out_dim, stage):
-    """the slice-major device layout (contiguous row sets per column slice) with the cp.async ring and with one
-    cp.async.bulk (TMA) copy per unit computes what the input-major default does"""
+@pytest.mark.parametrize("stage,flags", [(0, 2), (1, 2), (2, 2), (0, 4), (2, 4)])
+def test_layouts_and_bulk_stage(T, ops, mode, in_dim, out_dim, stage, flags):
+    """device layouts (2 = slice-major: contiguous row sets per column slice, the default; 4 = input-major) x staging
+    (2 = TMA pipeline with a producer warp, the default; 0 = per-warp cp.async rings; 1 = per-warp cp.async.bulk rings):
+    every combination computes the same operator (input-major weights always take the cp.async rings)"""
     w, r = conv(out_dim, in_dim)
     v = make_v(in_dim, 5)
     ctx = ops.default_context()
-    ew = make_weights(T, ops, r, in_dim, out_dim, flags=ops.SLICE_MAJOR)
+    ew = make_weights(T, ops, r, in_dim, out_dim, flags=flags)
     out = T.full((out_dim,), 9.0, dtype=T.float32, device="cuda")
     try:
         ctx.setOption("stage", stage)
@@ -273,19 +274,20 @@ def test_slice_major_layout_and_bulk_stage(T, ops, in_dim, out_dim, stage):
             assert ops.lastSelected() == res["n_selected"]
             assert rel_err(out.cpu().numpy(), res["out64"]) <= OUT_TOL
     finally:
-        ctx.setOption("stage", 0)
+        ctx.setOption("stage", 2)
 
 
-@pytest.mark.parametrize("opt,val", [("dynamic", 0), ("engine", 1)])
+@pytest.mark.parametrize("opt,val", [("dynamic", 1), ("engine", 1)])
 def test_engine_options_same_result(T, ops, opt, val):
     """static unit deal / the round-1 engine (fused kernel + integrate) against the oracle"""
     w, r = conv(4096, 14336)
-    ew = make_weights(T, ops, r, 14336, 4096)
+    ew = make_weights(T, ops, r, 14336, 4096, flags=ops.INPUT_MAJOR)
     v = make_v(14336)
     out = T.empty(4096, dtype=T.float32, device="cuda")
     ctx = ops.default_context()
     try:
         ctx.setOption(opt, val)
+        ctx.setOption("stage", 0)
         if opt == "engine":   # the round-1 engine only knows the bisection
             ctx.setCutoffMode("bisect")
             O.set_cutoff_mode("bisect")
@@ -294,7 +296,8 @@ def test_engine_options_same_result(T, ops, opt, val):
         assert ops.lastSelected() == res["n_selected"]
         assert rel_err(out.cpu().numpy(), res["out64"]) <= OUT_TOL
     finally:
-        ctx.setOption(opt, 1 if opt == "dynamic" else 2)
+        ctx.setOption(opt, 0 if opt == "dynamic" else 2)
+        ctx.setOption("stage", 2)
 
 
 def test_expert_number_selects_expert(T, ops, mode):

@@ -190,3 +190,95 @@ def test_native_loader_survives_corrupted_headers(tmp_path):
         probe()
     open(tmp_path / "f.safetensors", "wb").write(struct.pack("<Q", 2 ** 63) + bytes(raw))   # absurd header size
     probe()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# writer side: the C-ABI saver (effort_saver_*), convertMistral's name mapping, and the reference loader's name set
+# ---------------------------------------------------------------------------------------------------------
+def _fake_hf(n_layers, dim=32, hidden=64, kvd=16, vocab=48, seed=9):
+    rng = np.random.default_rng(seed)
+    t = {"model.norm.weight": rng.standard_normal(dim).astype(np.float16),
+         "lm_head.weight": rng.standard_normal((vocab, dim)).astype(np.float16),
+         "model.embed_tokens.weight": rng.standard_normal((vocab, dim)).astype(np.float16)}
+    for n in range(n_layers):
+        p = f"model.layers.{n}."
+        for name, shape in (("self_attn.q_proj.weight", (dim, dim)), ("self_attn.k_proj.weight", (kvd, dim)),
+                            ("self_attn.v_proj.weight", (kvd, dim)), ("self_attn.o_proj.weight", (dim, dim)),
+                            ("mlp.gate_proj.weight", (hidden, dim)), ("mlp.down_proj.weight", (dim, hidden)),
+                            ("mlp.up_proj.weight", (hidden, dim))):
+            t[p + name] = rng.standard_normal(shape).astype(np.float16)
+        t[p + "input_layernorm.weight"] = rng.standard_normal(dim).astype(np.float16)
+        t[p + "post_attention_layernorm.weight"] = rng.standard_normal(dim).astype(np.float16)
+    return t
+
+
+def _stub_bucketize(w):
+    """shape-faithful stand-in for effort_bucketize (the real one needs in >= 4096 and a GPU)"""
+    out, inn = w.shape
+    return {"buckets": np.zeros((inn * 16, max(1, out // 16)), np.float16), "bucket.stats": np.zeros((inn * 16, 4), np.float16),
+            "probes": np.zeros((4096,), np.float16)}
+
+
+@pytest.mark.parametrize("native", [True, False])
+def test_convert_mistral_writes_what_the_reference_loader_reads(tmp_path, native):
+    """convertMistral (convert.swift:59-127) name mapping from the HF checkpoint names, and the name set of the written
+    directory against what Model.init / Layer.init / ExpertWeights read (loader.swift:60-166, 201-272): every required
+    name present -- including attention `.core`, which the reference's attention loader reads unconditionally -- and
+    nothing outside required + optional."""
+    hf = _fake_hf(3)
+    index = W.convert_mistral(lambda n: hf[n], str(tmp_path), 3, _stub_bucketize, native=native)
+    wm = json.load(open(index))["weight_map"]
+    req, opt = W.reference_loader_names(3)
+    written = set(wm)
+    assert req <= written, sorted(req - written)[:5]
+    assert written <= req | opt, sorted(written - req - opt)[:5]
+    assert wm["output.core"] == wm["tok_embeddings.core"] == "buckets-FP16-00001-of-00003.safetensors"   # convert.swift:70-74
+    assert wm["layers.2.feed_forward.experts.0.w2.buckets"] == "buckets-FP16-00003-of-00003.safetensors"
+    L = W.TensorLoader(str(tmp_path))
+    assert np.array_equal(L["layers.1.attention.wk.core"], hf["model.layers.1.self_attn.k_proj.weight"])
+    assert np.array_equal(L["layers.2.ffn_norm"], hf["model.layers.2.post_attention_layernorm.weight"])
+    assert np.array_equal(L["layers.0.attention_norm"], hf["model.layers.0.input_layernorm.weight"])
+    assert np.array_equal(L["output.core"], hf["lm_head.weight"])
+    assert np.array_equal(L["tok_embeddings.core"], hf["model.embed_tokens.weight"])
+    # w1 = gate, w2 = down, w3 = up (convert.swift:98-104): the bucket row counts give the input dims away
+    assert L["layers.0.feed_forward.experts.0.w2.buckets"].shape[0] == 16 * 64
+    assert L["layers.0.feed_forward.experts.0.w1.buckets"].shape[0] == 16 * 32
+
+
+def test_native_saver_files_match_the_python_package(tmp_path):
+    """effort_saver_* (TensorSaver, safetensors.swift:38-85 / 222-280): files readable by the safetensors package and by
+    the library's own loader, byte-identical tensors, the reference's header metadata, index json; error codes."""
+    import ctypes as C
+    from effort_b200 import _lib
+    rng = np.random.default_rng(1)
+    files = [{"a.x": rng.standard_normal((5, 7)).astype(np.float16), "a.y": rng.standard_normal(11).astype(np.float32)},
+             {"b \"quoted\"": rng.standard_normal((2, 3, 4)).astype(np.float16), "b.empty": np.zeros((0, 4), np.float32)}]
+    s = W.NativeTensorSaver(str(tmp_path / "m"), "model")
+    for i, f in enumerate(files):
+        s.add_file(i, f)
+    with pytest.raises(TypeError):
+        s.add_file(0, {"bad": np.zeros(3, np.int32)})
+    Lc = _lib.load()
+    shape = (C.c_int64 * 1)(3)
+    z = np.zeros(3, np.float16)
+    assert Lc.effort_saver_add(s._h, 0, b"a.x", 0, 1, shape, z.ctypes.data, z.nbytes) == -5          # duplicate name
+    assert Lc.effort_saver_add(s._h, 0, b"short", 0, 1, shape, z.ctypes.data, 4) == -4               # bytes != shape
+    assert Lc.effort_saver_add(s._h, -1, b"neg", 0, 1, shape, z.ctypes.data, z.nbytes) == -1
+    index = s.save()
+    wm = json.load(open(index))["weight_map"]
+    assert wm == {"a.x": "model-00001-of-00002.safetensors", "a.y": "model-00001-of-00002.safetensors",
+                  "b \"quoted\"": "model-00002-of-00002.safetensors", "b.empty": "model-00002-of-00002.safetensors"}
+    from safetensors import safe_open
+    for i, f in enumerate(files):
+        path = str(tmp_path / "m" / W.file_name("model", i, 2))
+        with safe_open(path, framework="np") as r:
+            assert r.metadata() == {"description": "Bucket weights format, see mixtral-kolinko at github"}
+            assert set(r.keys()) == set(f)
+            for k, a in f.items():
+                got = r.get_tensor(k)
+                assert got.dtype == a.dtype and got.shape == a.shape and np.array_equal(got, a)
+    nl = W.NativeTensorLoader(str(tmp_path / "m"), "model")
+    for f in files:
+        for k, a in f.items():
+            assert np.array_equal(nl[k], a)
+    nl.close()
