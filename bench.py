@@ -13,6 +13,13 @@ north-star operating point); the same run also reports effort 1.0 and 0.5 in `ef
 Timing: W warm-up tokens (>= 3), then exactly K tokens between CUDA events on the launching stream with a
 barrier + synchronize on both sides, max over ranks.  Every token streams the selected rows of 14 GB of
 distinct weights (>> 126 MB L2), so no L2 flush is needed between iterations (config.l2).
+
+Besides the contract keys the line carries (rank 0, N = 1; each can be switched off, none touches the timed region):
+  quality   per-token logit cos-sim of the effort-e decode against a DENSE decode of the same tokens (every projection
+            through basicMul on the kept fp16 `core`; method: benchmarks/benchmark.swift:159-177, bar 0.99:
+            playground.swift:41), for the N(0, 0.02^2) weights of the headline run and for a heavy-tailed init
+  q4        BASELINE configs[2]: the Q4 model (bucketMulQ4 on wq/w1/w2/w3, dense wk/wv/wo) at effort 0.5
+  sweep     BASELINE configs[4]: raw bucketMul GEMVs 4096 x {4096, 11008, 14336} x effort 1.0 .. 0.1
 """
 from __future__ import annotations
 
@@ -30,6 +37,7 @@ METRIC = "Mistral-7B decode tok/s @ effort"
 SHAPES_PER_LAYER = [(4096, 4096), (4096, 1024), (4096, 1024), (4096, 4096), (4096, 14336), (4096, 14336), (14336, 4096)]
 DENSE_LM_HEAD_BYTES = 32000 * 4096 * 2
 BUCKET_BYTES_PER_TOKEN = 32 * sum(2 * i * o for i, o in SHAPES_PER_LAYER)  # 13.958 GB
+Q4_BUCKETED = ("wq", "w1", "w2", "w3")                                      # q4_convert.py:53,59
 
 
 def peaks():
@@ -43,14 +51,20 @@ def peaks():
 # ---------------------------------------------------------------------------------------------------------
 # CPU arm: the reference has no CPU implementation (Swift+Metal only) -> the oracle port, all host threads
 # ---------------------------------------------------------------------------------------------------------
-def cpu_layer_sample(effort: float, reps: int = 1, seed: int = 1234):
-    """One transformer layer's 7 GEMVs on the host cores, OpenMP on all of them (oracle port).  Returns a dict:
-    bucketmul_s / dense_s = seconds per layer for the bucketMul port at `effort` and for the dense fp16 GEMV
-    (basicMul, matrix.metal:150-162 -- the dense CPU baseline north_star asks for).  Weights: same synthetic
-    distribution, converted by the oracle."""
+def cpu_layer_sample(effort: float, reps: int = 5, seed: int = 1234):
+    """One transformer layer's 7 GEMVs on the host cores (oracle port, OpenMP, the reference's bisection cutoff).
+    Returns seconds per layer for the bucketMul port at `effort` and for the dense fp16 GEMV (basicMul,
+    matrix.metal:150-162 -- the dense CPU baseline north_star asks for): MEDIAN of `reps` repetitions after one warm-up,
+    min/max reported.  The thread count is fixed once: every CPU the process may run on (sched_getaffinity), threads
+    bound to cores (OMP_PROC_BIND / OMP_PLACES, set before the OpenMP runtime starts)."""
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
     import numpy as np
     from oracle import oracle as O
     from tests.util import make_v, make_w
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    O.set_threads(avail)
+    O.set_cutoff_mode("bisect")
     by_shape, dense = {}, {}
     for k, (i, o) in enumerate(sorted(set(SHAPES_PER_LAYER))):
         w = make_w(o, i, seed + k)
@@ -69,47 +83,43 @@ def cpu_layer_sample(effort: float, reps: int = 1, seed: int = 1234):
         for (i, o) in SHAPES_PER_LAYER:
             O.basic_mul_fast(vs[i], dense[(i, o)], outs[o])
 
-    # host threads: boxes expose 64-128 logical CPUs but cgroup quotas / SMT make "all of them" slower than fewer;
-    # take the fastest of a few counts on a short dense probe (the count used is reported as `cores`)
-    import os as _os
-    avail = len(_os.sched_getaffinity(0)) if hasattr(_os, "sched_getaffinity") else (_os.cpu_count() or 1)
-    best_t, best_dt = 1, float("inf")
-    for nt in sorted({avail, max(1, avail // 2), max(1, avail // 4), 32, 16, 8}):
-        if nt > avail:
-            continue
-        O.set_threads(nt)
-        O.basic_mul_fast(vs[4096], dense[(4096, 14336)], outs[14336])
-        t0 = time.perf_counter()
-        O.basic_mul_fast(vs[4096], dense[(4096, 14336)], outs[14336])
-        dt = time.perf_counter() - t0
-        if dt < best_dt:
-            best_t, best_dt = nt, dt
-    O.set_threads(best_t)
-    res = {}
-    for name, fn in (("bucketmul_s", run_bucket), ("dense_s", run_dense)):
-        fn()  # warm
-        t0 = time.perf_counter()
+    res = {"threads": O.num_threads(), "reps": reps}
+    for name, fn in (("bucketmul", run_bucket), ("dense", run_dense)):
+        fn()  # warm-up (page faults, thread pool)
+        ts = []
         for _ in range(reps):
+            t0 = time.perf_counter()
             fn()
-        res[name] = (time.perf_counter() - t0) / reps
-    res["threads"] = O.num_threads()
-    res["sample"] = "1 layer (7 GEMVs, 436 MB) x32 = 1 token; lm_head excluded"
+            ts.append(time.perf_counter() - t0)
+        ts.sort()
+        res[name + "_s"] = ts[len(ts) // 2]
+        res[name + "_min_s"], res[name + "_max_s"] = ts[0], ts[-1]
+    res["sample"] = f"1 layer (7 GEMVs, 436 MB of buckets) x32 = 1 token, median of {reps} reps after 1 warm-up; lm_head excluded"
     return res
+
+
+def cpu_record(r):
+    return {"value": 1.0 / (r["bucketmul_s"] * 32), "unit": "tok/s", "cores": r["threads"], "kind": "port", "sample": r["sample"],
+            "min": 1.0 / (r["bucketmul_max_s"] * 32), "max": 1.0 / (r["bucketmul_min_s"] * 32),
+            "dense_gemv_tok_s": 1.0 / (r["dense_s"] * 32),
+            "dense_gemv_min": 1.0 / (r["dense_max_s"] * 32), "dense_gemv_max": 1.0 / (r["dense_min_s"] * 32)}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     steps = max(1, args.steps)
-    r = cpu_layer_sample(args.effort, reps=max(1, min(steps, 3)))
-    tok_s = 1.0 / (r["bucketmul_s"] * 32)
+    r = cpu_layer_sample(args.effort, reps=5)
+    cb = cpu_record(r)
+    tok_s = cb["value"]
     line = {
         "impl": "reference", "metric": f"{METRIC} {args.effort}", "value": tok_s, "unit": "tok/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": r["bucketmul_s"] * 32 * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "fp16 weights, f32 accumulate", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {"value": tok_s, "unit": "tok/s", "cores": r["threads"], "kind": "port", "sample": r["sample"]},
-        "cpu_dense_gemv": {"value": 1.0 / (r["dense_s"] * 32), "unit": "tok/s", "cores": r["threads"],
+        "cpu_baseline": cb,
+        "cpu_dense_gemv": {"value": cb["dense_gemv_tok_s"], "unit": "tok/s", "cores": r["threads"], "min": cb["dense_gemv_min"],
+                           "max": cb["dense_gemv_max"],
                            "what": "dense fp16 GEMV (basicMul, matrix.metal:150-162) on the same layer sample"},
         "e2e": {"value": tok_s, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is Swift+Metal (no CPU path, not buildable here): CPU arm = oracle/ port of bucketMul, OpenMP",
@@ -131,6 +141,104 @@ def workload_config(args, world):
 # ---------------------------------------------------------------------------------------------------------
 # ours
 # ---------------------------------------------------------------------------------------------------------
+def student_t_w(nu: float = 3.0, scale: float = 0.02):
+    """Heavy-tailed synthetic init: every weight ~ scale * t_nu / sqrt(nu / (nu - 2)) (Student-t, unit variance before the
+    scale): same variance as the Gaussian init, a few weights per bucket carry most of the mass -- the regime real
+    transformer weights are in and the one the bucket order exploits."""
+    import torch
+
+    def fn(out_dim, in_dim, gen):
+        z = torch.randn((out_dim, in_dim), generator=gen, device="cuda", dtype=torch.float32)
+        # chi-square(nu) as a sum of nu squared normals (nu integer)
+        c = torch.zeros((out_dim, in_dim), device="cuda", dtype=torch.float32)
+        for _ in range(int(nu)):
+            c += torch.randn((out_dim, in_dim), generator=gen, device="cuda", dtype=torch.float32) ** 2
+        t = z / torch.sqrt(c / nu)
+        return (t * (scale / (nu / (nu - 2.0)) ** 0.5)).half()
+    return fn
+
+
+def decode_quality(model_factory, dense_factory, effort, n_tokens):
+    """Logit cos-sim, token by token, of the effort-e decode vs a dense decode fed the SAME tokens."""
+    import numpy as np
+    import torch
+    from oracle import oracle as O
+    m = model_factory()
+    m.reset()
+    toks, logits_e = [1], []
+    buf = np.zeros(m.cfg.vocab, np.float32)
+    nxt = m.step_host(1, effort, buf)
+    logits_e.append(buf.copy())
+    for _ in range(n_tokens - 1):
+        toks.append(nxt)
+        nxt = m.step_host(nxt, effort, buf)
+        logits_e.append(buf.copy())
+    d = dense_factory(m)
+    d.reset()
+    cs = []
+    for t, le in zip(toks, logits_e):
+        d.step_host(t, 1.0, buf)
+        cs.append(O.cossim(le, buf))
+    del d
+    torch.cuda.empty_cache()
+    return {"min": float(min(cs)), "mean": float(sum(cs) / len(cs)), "tokens": len(cs)}
+
+
+def dense_twin(model):
+    """Every projection as a Q4-kind ExpertWeights WITHOUT buckets: expertMul routes those to basicMul on `core`
+    (expertMul.swift:26-31) -- the dense fp16 decode the quality is measured against."""
+    from effort_b200 import ops
+    from effort_b200.model import DecodeModel
+    d = DecodeModel(model.cfg, model.ctx)
+    for i, L in enumerate(model.layers):
+        ews = [ops.ExpertWeights(core=w, inDim=w.shape[1], outDim=w.shape[0], kind=ops.KIND_Q4) for w in model.dense[i]]
+        d.set_layer(i, *ews, L[7], L[8])
+    d.set_head(*model.head)
+    return d
+
+
+def gemv_sweep(stream, shapes, efforts, peak):
+    """BASELINE configs[4]: raw bucketMul GEMVs, graph replay over rotating weight copies (> 2x L2)."""
+    import torch
+    from effort_b200 import ops
+    from tools.sweep import make_v_gpu, rand_weights
+    rows = []
+    for (in_dim, out_dim) in shapes:
+        mat_bytes = 2 * in_dim * out_dim
+        copies = max(2, -(-(300 << 20) // mat_bytes))
+        ws = [rand_weights(out_dim, in_dim, 100 + c)[0] for c in range(copies)]
+        torch.cuda.empty_cache()
+        v = make_v_gpu(in_dim)
+        out = torch.empty(out_dim, dtype=torch.float32, device="cuda")
+        iters = 3 * copies
+        for eff in efforts:
+            for k in range(copies):
+                ops.bucketMul(v, ws[k], None, out, eff)
+            torch.cuda.synchronize()
+            nsel = ops.lastSelected()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for k in range(iters):
+                    ops.bucketMul(v, ws[k % copies], None, out, eff)
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 8
+            e0.record(stream)
+            for _ in range(reps):
+                g.replay()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / (reps * iters)
+            alg = eff * mat_bytes
+            rows.append({"shape": f"{in_dim}x{out_dim}", "effort": eff, "us": round(us, 2), "GBs": round(alg / us / 1e3, 1),
+                         "frac": round(alg / us / 1e3 / peak, 3), "selected_frac": round(nsel / (in_dim * 16), 4)})
+        del ws
+        torch.cuda.empty_cache()
+    return rows
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -147,11 +255,13 @@ def run_ours(args, rank, local_rank, world):
         init_comm(ops.default_context(), rank, world)
     streams_total = 1 if tp else world   # independent token streams in the job
     stream = torch.cuda.Stream()
+    want_quality = rank == 0 and world == 1 and not args.quick and not args.no_quality
     with torch.cuda.stream(stream):
+        cfg = MistralConfig(n_layers=args.layers)
         if tp:   # one model, column/row sharded over the ranks (same seed everywhere)
-            model = DecodeModel.random_init(MistralConfig(n_layers=args.layers), seed=1234, tp_rank=rank, tp_size=world)
+            model = DecodeModel.random_init(cfg, seed=1234, tp_rank=rank, tp_size=world)
         else:
-            model = DecodeModel.random_init(MistralConfig(n_layers=args.layers), seed=1234 + rank)
+            model = DecodeModel.random_init(cfg, seed=1234 + rank, keep_dense=want_quality)
         torch.cuda.synchronize()
 
         def barrier():
@@ -214,6 +324,33 @@ def run_ours(args, rank, local_rank, world):
                 extras[str(eff)] = max(8, args.steps // 4) / (ms_e / 1e3)
         extras[str(args.effort)] = tok_s / streams_total
 
+        # tensor parallel: the sharded model must compute what the unsharded one does (rank 0 holds both)
+        tp_check = None
+        if tp and not args.quick:
+            ref_model = DecodeModel.random_init(cfg, seed=1234) if rank == 0 else None
+            model.reset()
+            cs_tp = []
+            tok = torch.tensor([1], dtype=torch.int32, device="cuda")
+            if rank == 0:
+                ref_model.reset()
+            for _ in range(4):
+                model.step(tok, args.effort)
+                torch.cuda.synchronize()
+                if rank == 0:
+                    ref_model.step(tok, args.effort)
+                    torch.cuda.synchronize()
+                    a, b = model.logits().double(), ref_model.logits().double()
+                    cs_tp.append(float((a @ b) / (a.norm() * b.norm())))
+                    tok = torch.tensor([ref_model.next_token()], dtype=torch.int32, device="cuda")
+                tl = [int(tok.item())]
+                dist.broadcast_object_list(tl, src=0)
+                tok = torch.tensor(tl, dtype=torch.int32, device="cuda")
+            if rank == 0:
+                tp_check = {"logit_cos_sim_vs_unsharded": cs_tp, "tokens": 4}
+                assert min(cs_tp) > 0.99, f"tensor-parallel logits diverge from the unsharded model: {cs_tp}"
+                del ref_model
+                torch.cuda.empty_cache()
+
         # roofline of the dominant operator: bucketMul 4096 -> 14336 (w1/w3; 50 % of the bucket bytes with w2)
         roof = None
         if rank == 0:
@@ -241,36 +378,123 @@ def run_ours(args, rank, local_rank, world):
             us = e0.elapsed_time(e1) * 1e3 / (reps * len(w1s))
             alg = args.effort * r_in * r_out * 2
             ach = alg / us / 1e3
-            traffic = None
-            try:  # dram__bytes_read+write per launch of the fused kernel from the committed ncu --set full capture
-                tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            traffic, traffic_src = None, None
+            try:  # dram__bytes_read+write per launch of the kernel from the committed ncu --set full capture (not re-measured here)
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
                 traffic = tr.get(str(args.effort)) if world == 1 else None
+                traffic_src = tr.get("source")
             except Exception:
                 pass
             roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "kernel": f"bucketMul {r_in}->{r_out} (bucket_mul_fused_kernel + integrate_kernel)",
+                    "traffic_source": traffic_src,
+                    "kernel": f"bucketMul {r_in}->{r_out}: one launch of the fused round-2 kernel (cutoff + selection + TMA-staged "
+                              f"gather-MAC + reductions into out)",
                     "us_per_launch": us, "algorithmic_bytes": alg, "peak_source": peak_src}
+
+        def guarded(fn):
+            try:
+                return fn()
+            except Exception as e:  # an optional record must never cost the headline line
+                return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+        quality = q4 = sweep = None
+        if want_quality:
+            def q_headline():
+                return decode_quality(lambda: model, dense_twin, args.effort, min(args.steps, 16))
+            quality = {"what": "per-token logit cos-sim, effort-e decode vs dense fp16 decode (basicMul on core) of the same tokens",
+                       "effort": args.effort,
+                       "gaussian N(0, 0.02^2) (headline weights)": guarded(q_headline)}
+            model.dense = None
+            torch.cuda.empty_cache()
+
+        if rank == 0 and world == 1 and not args.quick and not args.no_extras:
+            peak, _ = peaks()
+            # free the headline model first: the extra records build their own
+            del model
+            torch.cuda.empty_cache()
+
+            def q_heavy():
+                hm = DecodeModel.random_init(cfg, seed=77, keep_dense=True, weight_fn=student_t_w(3.0))
+                r = {e: decode_quality(lambda: hm, dense_twin, e, min(args.steps, 16)) for e in (args.effort, 0.5)}
+                del hm
+                torch.cuda.empty_cache()
+                return r
+            if quality is not None:
+                quality["student-t(nu=3) * 0.02/sqrt(3), same variance as the Gaussian init"] = guarded(q_heavy)
+
+            def q4_record():
+                qm = DecodeModel.random_init_q4(cfg, seed=4321)
+                qm.reset()
+                tok = torch.tensor([1], dtype=torch.int32, device="cuda")
+                qm.step(tok, 0.5)
+                for _ in range(4):
+                    qm.step(None, 0.5)
+                torch.cuda.synchronize()
+                n = max(8, args.steps // 2)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(n):
+                    qm.step(None, 0.5)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                tps = n / (e0.elapsed_time(e1) / 1e3)
+                # Q4 roofline operator: bucketMulQ4 4096 -> 14336 (w1), effort * in * out * 0.5 bytes of nibbles
+                w1s = [L[4] for L in qm.layers]
+                v = torch.randn(4096, device="cuda", dtype=torch.float32)
+                out = torch.empty(14336, device="cuda", dtype=torch.float32)
+                g = torch.cuda.CUDAGraph()
+                for w in w1s[:2]:
+                    ops.expertMul(v, w, None, out, 0.5)
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g, stream=stream):
+                    for w in w1s:
+                        ops.expertMul(v, w, None, out, 0.5)
+                g.replay()
+                torch.cuda.synchronize()
+                e0.record(stream)
+                for _ in range(5):
+                    g.replay()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                us = e0.elapsed_time(e1) * 1e3 / (5 * len(w1s))
+                alg = 0.5 * 4096 * 14336 * 0.5
+                bytes_tok = args.layers * (0.5 * 0.5 * (4096 * 4096 + 3 * 4096 * 14336) + 2 * (2 * 4096 * 1024 + 4096 * 4096)) + DENSE_LM_HEAD_BYTES
+                del qm
+                torch.cuda.empty_cache()
+                return {"workload": "Mistral-7B Q4 single-stream decode (BASELINE configs[2]): bucketMulQ4 + outliers on wq/w1/w2/w3, "
+                                    "dense fp16 core on wk/wv/wo (q4_convert.py:53), effort 0.5", "value": tps, "unit": "tok/s",
+                        "roofline": {"kernel": "expertMul Q4 4096->14336 (fused kernel + calcOutliers)", "us_per_launch": us,
+                                     "algorithmic_bytes": alg, "achieved": alg / us / 1e3, "unit": "GB/s", "frac": alg / us / 1e3 / peak,
+                                     "note": "outlier records (16 B x 2 % of the weights = 18.8 MB) are streamed on top of the nibbles"},
+                        "token_bytes": bytes_tok, "token_roofline_frac": tps / (peak * 1e9 / bytes_tok)}
+            q4 = guarded(q4_record)
+
+            def sweep_record():
+                effs = [1.0, 0.9, 0.8, 0.7, 0.6, 0.5, 0.4, 0.3, 0.25, 0.2, 0.1]
+                return {"what": "raw bucketMul GEMV (BASELINE configs[4]), one fused launch per call, graph replay over weight "
+                                "copies > 2x L2", "rows": gemv_sweep(stream, [(4096, 4096), (4096, 11008), (4096, 14336)], effs, peak)}
+            sweep = guarded(sweep_record)
 
         cpu = None
         if rank == 0 and world == 1 and not args.no_cpu:  # CPU baseline on rank 0 at N=1 only
-            r = cpu_layer_sample(args.effort, reps=1)
-            cpu = {"value": 1.0 / (r["bucketmul_s"] * 32), "unit": "tok/s", "cores": r["threads"], "kind": "port",
-                   "sample": r["sample"], "dense_gemv_tok_s": 1.0 / (r["dense_s"] * 32)}
+            cpu = cpu_record(cpu_layer_sample(args.effort, reps=5))
 
         if rank == 0:
             peak, _ = peaks()
             bytes_tok = args.effort * BUCKET_BYTES_PER_TOKEN * args.layers / 32 + DENSE_LM_HEAD_BYTES
+            roof_tok_s = peak * 1e9 / bytes_tok * (world if tp else 1)   # TP: every rank streams 1/world of the bytes
             line = {
                 "metric": f"{METRIC} {args.effort}", "value": tok_s, "unit": "tok/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong" if (tp or world == 1) else "weak", "vs_baseline": None, "dtype": "fp16 weights, f32 accumulate",
                 "data": "synthetic", "config": workload_config(args, world),
-                "e2e": {"value": e2e_tok_s, "unit": "tok/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4 + 4 * model.cfg.vocab},
+                "e2e": {"value": e2e_tok_s, "unit": "tok/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4 + 4 * cfg.vocab},
                 "gpu_launches": int(launches),
                 "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
                 "roofline": roof, "cpu_baseline": cpu, "efforts": extras,
-                "token_roofline": {"bytes_per_token": bytes_tok, "tok_s_at_peak": peak * 1e9 / bytes_tok,
-                                   "frac": (tok_s / streams_total) / (peak * 1e9 / bytes_tok / (world if tp else 1))},
+                "token_roofline": {"bytes_per_token": bytes_tok, "tok_s_at_peak": roof_tok_s,
+                                   "frac": (tok_s / streams_total) / roof_tok_s},
+                "quality": quality, "q4": q4, "sweep": sweep, "tp_check": tp_check,
             }
             print(json.dumps(line), flush=True)
     if world > 1:
@@ -285,8 +509,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--effort", type=float, default=0.25)
     ap.add_argument("--layers", type=int, default=32)
-    ap.add_argument("--quick", action="store_true", help="skip the effort 1.0 / 0.5 extras")
+    ap.add_argument("--quick", action="store_true", help="headline only: no effort 1.0 / 0.5, quality, q4, sweep records")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-quality", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the heavy-tail quality, q4 and sweep records")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas instead of tensor parallelism")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -49,6 +49,7 @@ SIGNATURES = {
     "effort_comm_p2p_local_handle": (C.c_int, [vp, vp]),
     "effort_comm_p2p_disable": (C.c_int, [vp]),
     "effort_comm_p2p_connect": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+    "effort_comm_p2p_collective": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_size_t, vp]),
     "effort_comm_all_reduce": (C.c_int, [vp, vp, C.c_size_t, vp]),
     "effort_comm_all_gather": (C.c_int, [vp, vp, vp, C.c_size_t, vp]),
     "effort_model_create": (C.c_int, [vp, vp, C.POINTER(C.c_void_p)]),

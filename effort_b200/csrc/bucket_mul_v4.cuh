@@ -1,0 +1,502 @@
+// bucket_mul_v4.cuh -- the fused bucketMul for FP16 buckets in the slice-major device layout (the default path).
+//
+// Same operator as bucket_mul_v2_kernel (cutoff -> selection -> gather-MAC -> reductions into `out`; reference:
+// BucketMul.fullMul, bucketMul.swift:34-88 and bucketMul.metal:11-247).  What the measurements of rounds 1-2 asked for
+// (profiles/r02_*): the accumulate loop is ISSUE bound (every weight costs a shift, a LOP3, a convert, an LDS, an FFMA
+// and an STS), so everything that is not those six instructions has to leave the accumulating warps, and the serial
+// prologue has to shrink.
+//
+//  * 8 CONSUMER warps (0-7), each with a private 8 KB accumulator tile, do nothing but wait for a unit, read its rows
+//    and run the read-modify-writes (four rows = 16 independent updates per lane at a time);
+//  * 8 PRODUCER warps (8-15), one per consumer: a producer takes the next input from a shared ticket counter (work
+//    stealing: a consumer that drains faster gets more), looks up its selection mask and -- slice-major layout: the
+//    ranks an input selects inside this CTA's column slice are contiguous -- copies the whole run (1..16 rows) with
+//    16-byte cp.async into the next slot of the pair's private ring; completion reaches the consumer through an
+//    mbarrier (cp.async.mbarrier.arrive.noinc), the slot comes back through a second one.  Units are whole inputs, so
+//    the per-unit cost is paid once per ~6 rows at effort 0.25 and once per 16 rows at effort 1.0, no list is built,
+//    and up to 8 x 4 x 4 KB are in flight per SM.
+//  * the exact-select cutoff runs on FOUR warps (one per scheduler, 32 products per lane, a 128-thread named barrier
+//    per round) while the other twelve zero the tiles, fetch their stats and inputs and run the overwrite protocol.
+#pragma once
+#include "bucket_mul_v3.cuh"
+
+namespace effort {
+
+constexpr int kV4Pairs = 8;                    // consumer / producer warp pairs
+constexpr int kV4Slots = 4;                    // ring slots per pair
+constexpr int kV4SlotData = 16 * 256;          // up to 16 rows of a full-width slice
+constexpr int kV4SlotBytes = kV4SlotData + 128;  // + header {val, n rows, row stride}, slots stay 128-byte aligned
+constexpr int kV4SelWarps = 4;
+
+struct V4Header {
+    CutoffSmem cut;                      // bisect mode scratch
+    uint2 sel_slot[2][kV4SelWarps];      // select mode: per-warp packed counts, double buffered by round parity
+    float red[kV4SelWarps];
+    float cutoff, denom;
+    int sel_rows;
+    unsigned ticket;                     // next input a producer may take
+    unsigned long long full_bar[kV4Pairs][kV4Slots];
+    unsigned long long empty_bar[kV4Pairs][kV4Slots];
+};
+
+struct V4Smem {
+    static constexpr int kTileFloats = 16 * 32 * 4;
+    static constexpr int kTileBytes = kTileFloats * 4;
+    static constexpr size_t kHdrBytes = (sizeof(V4Header) + 127) & ~size_t(127);
+    static constexpr size_t kBytes = (size_t)kTileBytes /*alignment slack*/ + (size_t)kV4Pairs * kTileBytes + kHdrBytes +
+                                     (size_t)kV2MaxInputs * (4 + 4 + 4) + 128 + (size_t)kV4Pairs * kV4Slots * kV4SlotBytes;
+};
+
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// count of keys above the threshold, 32 keys (16 bf16x2 registers) per thread
+__device__ __forceinline__ uint32_t count_gt32(const uint32_t (&keys)[16], uint32_t th) {
+    const __nv_bfloat162 t = as_bf162(splat_bf16(th));
+    __nv_bfloat162 c0 = __hgt2(as_bf162(keys[0]), t), c1 = __hgt2(as_bf162(keys[1]), t);
+#pragma unroll
+    for (int i = 2; i < 16; i += 2) {
+        c0 = __hadd2(c0, __hgt2(as_bf162(keys[i]), t));
+        c1 = __hadd2(c1, __hgt2(as_bf162(keys[i + 1]), t));
+    }
+    return (uint32_t)bf162_count(__hadd2(c0, c1));  // 0..32
+}
+
+// exact select on the first kV4SelWarps warps (gt = thread index inside the group): see select_cutoff (bucket_mul_v2.cuh)
+__device__ __forceinline__ float select_cutoff_group(const uint32_t (&keys)[16], int k, V4Header& hdr, int gt) {
+    const int lane = gt & 31, gw = gt >> 5;
+    uint32_t u = 0;
+    bool any = true;
+    const unsigned need = (unsigned)(k + 1);
+#pragma unroll 1
+    for (int round = 0; round < 8; round++) {
+        const int b = 14 - 2 * round;
+        uint32_t th1, th2, th3;
+        if (round == 0) { th1 = 0u; th2 = 1u << 14; th3 = 0x7FFFu; }
+        else { th1 = u | (1u << b); th2 = u | (2u << b); th3 = u | (3u << b); }
+        const uint32_t c1 = count_gt32(keys, th1), c2 = count_gt32(keys, th2), c3 = count_gt32(keys, th3);
+        const uint32_t a = __reduce_add_sync(0xffffffffu, c1 | (c2 << 16));
+        const uint32_t bsum = __reduce_add_sync(0xffffffffu, c3);
+        if (lane == 0) hdr.sel_slot[round & 1][gw] = make_uint2(a, bsum);
+        asm volatile("bar.sync 2, %0;" ::"n"(kV4SelWarps * 32) : "memory");
+        uint32_t A = 0, B = 0;
+#pragma unroll
+        for (int w = 0; w < kV4SelWarps; w++) {
+            const uint2 s = hdr.sel_slot[round & 1][w];
+            A += s.x;
+            B += s.y;
+        }
+        const unsigned g1 = A & 0xFFFFu, g2 = A >> 16, g3 = B;
+        if (round == 0) {
+            any = g1 >= need;
+            if (g2 >= need) u = 1u << 14;
+        } else {
+            const unsigned j = (g1 >= need ? 1u : 0u) + (g2 >= need ? 1u : 0u) + (g3 >= need ? 1u : 0u);
+            u |= j << b;
+        }
+    }
+    const uint32_t t = any ? (u + 1u) : 0u;
+    return __uint_as_float(t << 16);
+}
+
+template <int CUT>
+__global__ void __launch_bounds__(kV2Threads, 1)
+bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int SLOTS = 16, VEC = 4;
+    constexpr int NT = kV2Threads, NC = kV4Pairs;
+    constexpr int TF = V4Smem::kTileFloats, TW = 32 * VEC, LB = VEC * 2;
+    constexpr int kRow = 32 * LB;  // 256 bytes: a full-width row slice
+
+    int pi = 0;
+#pragma unroll
+    for (int k = 1; k < kMulBatchMax; k++) pi += (k < batch.n && (int)blockIdx.x >= batch.cta_begin[k]) ? 1 : 0;
+    const V2Problem& pb = batch.p[pi];
+    const int lb = (int)blockIdx.x - batch.cta_begin[pi];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool consumer = warp < NC;
+    const int pair = warp & (NC - 1);
+    const bool sel_warp = warp < kV4SelWarps;
+    const int slice = lb % pb.CS, rsp = lb / pb.CS;
+    const int RS = pb.RS, P = pb.P, C = pb.C;
+
+    // ---- carve shared memory ----
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t s1 = (s0 + (uint32_t)V4Smem::kTileBytes - 1u) & ~((uint32_t)V4Smem::kTileBytes - 1u);
+    unsigned char* p = smem_raw + (s1 - s0);
+    float* tiles = reinterpret_cast<float*>(p);
+    const uint32_t tiles_saddr = s1;
+    p += (size_t)NC * V4Smem::kTileBytes;
+    V4Header& hdr = *reinterpret_cast<V4Header*>(p);
+    p += V4Smem::kHdrBytes;
+    uint32_t* sbase = reinterpret_cast<uint32_t*>(p);
+    p += (size_t)kV2MaxInputs * 4;
+    float* sval = reinterpret_cast<float*>(p);
+    p += (size_t)kV2MaxInputs * 4;
+    uint32_t* smask = reinterpret_cast<uint32_t*>(p);
+    p += (size_t)kV2MaxInputs * 4;
+    p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 127) & ~uintptr_t(127));
+    float* ring_f = reinterpret_cast<float*>(p);
+    const uint32_t ring_saddr = (uint32_t)__cvta_generic_to_shared(p) + (uint32_t)pair * (uint32_t)(kV4Slots * kV4SlotBytes);
+
+    pdl_trigger();
+    if (pb.exp_no) pdl_wait();
+    const uint32_t e_no = pb.exp_no ? *pb.exp_no : 0u;
+    V2_TRACE(0);
+
+    // ---- 0. constant metadata before the dependency wait ----
+    const uint64_t keep = l2_policy_evict_last();
+    const int n_in = (pb.in > rsp) ? (pb.in - 1 - rsp) / RS + 1 : 0;
+    float sel_stat[16];
+#pragma unroll
+    for (int rho = 0; rho < 16; rho++) sel_stat[rho] = 0.f;
+    auto load_stats = [&](int j, float (&st)[16]) {
+        const int i = rsp + j * RS;
+        if (P == 16) {
+            const uint4* sp = reinterpret_cast<const uint4*>(pb.st16 + ((size_t)e_no * pb.in + i) * 16);
+            const uint4 a = ldg_keep_u4(sp, keep), b = ldg_keep_u4(sp + 1, keep);
+            const uint32_t ws[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int q2 = 0; q2 < 8; q2++) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ws[q2]));
+                st[2 * q2] = f.x;
+                st[2 * q2 + 1] = f.y;
+            }
+        } else {
+#pragma unroll
+            for (int rho = 0; rho < 16; rho++)
+                if (rho < P) st[rho] = __half2float(pb.st16[((size_t)e_no * pb.in + i) * P + rho]);
+        }
+    };
+    if (tid < n_in) load_stats(tid, sel_stat);
+    const int vmode = pb.norm_w ? kVNorm : (pb.v2 ? kVSilu : kVPlain);
+    uint4 prb[4], nwv[4];
+    if (CUT == kCutSelect && sel_warp) {  // 32 consecutive probes (and norm weights) per thread of the select group
+        const uint4* pp = reinterpret_cast<const uint4*>(pb.probes + (size_t)e_no * EFFORT_PROBES_MAX) + 4 * tid;
+#pragma unroll
+        for (int c = 0; c < 4; c++) prb[c] = ldg_keep_u4(pp + c, keep);
+        if (vmode == kVNorm) {
+            const uint4* np4 = reinterpret_cast<const uint4*>(pb.norm_w) + 4 * tid;
+#pragma unroll
+            for (int c = 0; c < 4; c++) nwv[c] = np4[c];
+        }
+    }
+    if (warp == NC) {  // first producer warp: the ring barriers
+        for (int s = lane; s < NC * kV4Slots; s += 32) {
+            mbar_init((uint32_t)__cvta_generic_to_shared(&hdr.full_bar[0][0] + s), 33);  // 32 cp.async arrivals + the header's
+            mbar_init((uint32_t)__cvta_generic_to_shared(&hdr.empty_bar[0][0] + s), 1);
+        }
+        if (lane == 0) { hdr.ticket = 0u; hdr.sel_rows = 0; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    V2_TRACE(1);
+    pdl_wait();
+
+    // ---- 1. inputs.  Select group: 32 entries per thread for the cutoff; everybody: the thread's own input dim ----
+    const int slice_cols = min(pb.W, C - slice * pb.W);
+    float my_v = 0.f, my_x3 = 0.f, my_nw = 1.f;
+    if (tid < n_in) {
+        const int i = rsp + tid * RS;
+        my_v = pb.v[i];
+        if (vmode == kVSilu) my_x3 = pb.v2[i];
+        if (vmode == kVNorm) my_nw = __half2float(pb.norm_w[i]);
+    }
+    if constexpr (CUT == kCutSelect) {
+        if (sel_warp) {
+            const float* src = (vmode == kVPlain) ? pb.v_cut : pb.v;
+            float vv[32];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const float4 a = *reinterpret_cast<const float4*>(src + 32 * tid + 4 * c);
+                vv[4 * c] = a.x; vv[4 * c + 1] = a.y; vv[4 * c + 2] = a.z; vv[4 * c + 3] = a.w;
+            }
+            if (vmode == kVSilu) {
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const float4 a = *reinterpret_cast<const float4*>(pb.v2 + 32 * tid + 4 * c);
+                    vv[4 * c] = silu_mul(vv[4 * c], a.x); vv[4 * c + 1] = silu_mul(vv[4 * c + 1], a.y);
+                    vv[4 * c + 2] = silu_mul(vv[4 * c + 2], a.z); vv[4 * c + 3] = silu_mul(vv[4 * c + 3], a.w);
+                }
+            }
+            float denom = 1.f;
+            if (vmode == kVNorm) {  // rmsNorm32fast (aux.metal:113-152) over the 4096 entries the group holds
+                float ss = 0.f;
+#pragma unroll
+                for (int m = 0; m < 32; m++) ss += vv[m] * vv[m];
+                ss = warp_sum_f(ss);
+                if (lane == 0) hdr.red[warp] = ss;
+                asm volatile("bar.sync 2, %0;" ::"n"(kV4SelWarps * 32) : "memory");
+                float t = 0.f;
+#pragma unroll
+                for (int w = 0; w < kV4SelWarps; w++) t += hdr.red[w];
+                denom = sqrtf(t / (float)pb.in + pb.norm_eps);
+                if (tid == 0) hdr.denom = denom;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const uint32_t nw[4] = {nwv[c].x, nwv[c].y, nwv[c].z, nwv[c].w};
+#pragma unroll
+                    for (int m = 0; m < 4; m++) {
+                        const float2 wf = __half22float2(*reinterpret_cast<const __half2*>(&nw[m]));
+                        vv[8 * c + 2 * m] = (vv[8 * c + 2 * m] / denom) * wf.x;
+                        vv[8 * c + 2 * m + 1] = (vv[8 * c + 2 * m + 1] / denom) * wf.y;
+                    }
+                }
+            }
+            uint32_t keys[16];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float v8[8] = {vv[8 * c], vv[8 * c + 1], vv[8 * c + 2], vv[8 * c + 3], vv[8 * c + 4], vv[8 * c + 5], vv[8 * c + 6], vv[8 * c + 7]};
+                uint32_t k4[4];
+                score8(v8, prb[c], k4);
+                keys[4 * c] = k4[0]; keys[4 * c + 1] = k4[1]; keys[4 * c + 2] = k4[2]; keys[4 * c + 3] = k4[3];
+            }
+            V2_TRACE(3);
+            const float cut = select_cutoff_group(keys, EFFORT_PROBES_MAX - pb.q, hdr, tid);
+            if (tid == 0) hdr.cutoff = cut;
+        }
+    }
+    if (!sel_warp || CUT != kCutSelect) {
+        // the other warps meanwhile: zero the 8 accumulator tiles, run the overwrite protocol
+        const int nz = (CUT == kCutSelect) ? (NT - kV4SelWarps * 32) : NT, z0 = (CUT == kCutSelect) ? tid - kV4SelWarps * 32 : tid;
+        float4* t4 = reinterpret_cast<float4*>(tiles);
+        for (int i = z0; i < NC * TF / 4; i += nz) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (warp == NT / 32 - 1 && pb.out_mode == kOutOverwrite) {
+            // overwrite semantics: zero this CTA's share of the slice's outputs, make the zeros visible, arrive on the
+            // slice counter -- inspected right before the reductions at the end of the kernel
+            const int n4 = slice_cols * SLOTS / 4, per = (n4 + RS - 1) / RS;
+            float4* o4 = reinterpret_cast<float4*>(pb.out + (size_t)slice * pb.W * SLOTS);
+            for (int x = rsp * per + lane; x < min(n4, (rsp + 1) * per); x += 32) o4[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                atomicAdd(pb.sync + 2 * slice, 1u);
+            }
+        }
+    }
+    V2_TRACE(2);
+    float denom = 1.f;
+    if constexpr (CUT != kCutSelect) {
+        // bit-exact replay of the reference's bisection by four warps (cutoff.cuh)
+        if (vmode == kVNorm) {  // the group path scores (v / denom) * w itself: it needs the denominator first
+            float ss = 0.f;
+            for (int i = tid; i < pb.in; i += NT) { const float x = pb.v[i]; ss += x * x; }
+            ss = warp_sum_f(ss);
+            float* redf = ring_f;  // the rings are idle
+            if (lane == 0) redf[warp] = ss;
+            __syncthreads();
+            float t = (lane < NT / 32) ? redf[lane] : 0.f;
+            t = warp_sum_f(t);
+            denom = sqrtf(t / (float)pb.in + pb.norm_eps);
+            __syncthreads();
+        }
+        float* vtmp = ring_f;
+        if (vmode == kVSilu) {
+            for (int i = tid; i < EFFORT_PROBES_MAX; i += NT) vtmp[i] = silu_mul(pb.v[i], pb.v2[i]);
+            __syncthreads();
+        }
+        if (tid < kCutThreads) {
+            GroupProbes gpr;
+            group_load_probes(pb.probes + (size_t)e_no * EFFORT_PROBES_MAX, EFFORT_PROBES_MAX, tid, gpr, keep);
+            GroupProducts gp;
+            if (vmode == kVNorm) group_score<true>(pb.v, gpr, EFFORT_PROBES_MAX, tid, gp, pb.norm_w, denom);
+            else if (vmode == kVPlain) group_score<false>(pb.v_cut, gpr, EFFORT_PROBES_MAX, tid, gp, nullptr, 1.f);
+            else group_score<false>(vtmp, gpr, EFFORT_PROBES_MAX, tid, gp, nullptr, 1.f);
+            group_cutoff<1>(gp, EFFORT_PROBES_MAX, pb.q, hdr.cut, tid, nullptr);
+            if (tid == 0) { hdr.cutoff = hdr.cut.result; hdr.denom = denom; }
+        }
+    }
+    __syncthreads();  // cutoff and denominator known; tiles zeroed; barriers initialised
+    const float cutoff = hdr.cutoff;
+    if (vmode == kVNorm) {
+        denom = hdr.denom;
+        my_v = (my_v / denom) * my_nw;
+    } else if (vmode == kVSilu) {
+        my_v = silu_mul(my_v, my_x3);
+    }
+    if (pb.cutoff_out && lb == 0 && tid == 0) *pb.cutoff_out = cutoff;
+    V2_TRACE(6);
+
+    const int seg_bytes = slice_cols * 2;
+    const bool full_width = slice_cols == TW;
+    const int lpr = pb.lpr, R = pb.R;
+    const int rowslot = lane / lpr, lcol = lane % lpr;
+    const bool col_ok = lcol * VEC < slice_cols;
+    const uint32_t base_lane = (tiles_saddr + (uint32_t)pair * V4Smem::kTileBytes) | (uint32_t)(lane * 4);
+    const uint64_t pol = l2_policy_evict_first();
+    const uint4* bk16 = reinterpret_cast<const uint4*>(pb.bk + (size_t)pb.in * P * ((size_t)slice * pb.W));  // slice-major
+    const uint32_t rs16 = (uint32_t)(seg_bytes >> 4);
+
+    int slot = 0, filled = 0;
+    uint32_t phase = 0u;  // consumer: full-barrier parities; producer: empty-barrier parities (bit per slot)
+    // ---- passes over the inputs of this row split (one pass for every Mistral shape) ----
+    for (int j0 = 0; j0 < n_in; j0 += NT) {
+        const int j = j0 + tid;
+        if (j0 > 0) {
+            __syncthreads();
+#pragma unroll
+            for (int rho = 0; rho < 16; rho++) sel_stat[rho] = 0.f;
+            my_v = 0.f;
+            if (j < n_in) {
+                load_stats(j, sel_stat);
+                const int i = rsp + j * RS;
+                my_v = pb.v[i];
+                if (vmode == kVNorm) my_v = (my_v / denom) * __half2float(pb.norm_w[i]);
+                else if (vmode == kVSilu) my_v = silu_mul(my_v, pb.v2[i]);
+            }
+            if (tid == 0) hdr.ticket = 0u;
+        }
+        // 2. selection mask of this thread's input (prepareDispatch, bucketMul.metal:66)
+        unsigned mask = 0u;
+#pragma unroll
+        for (int rho = 0; rho < 16; rho++)
+            if (rho < P && j < n_in && row_selected(cutoff, sel_stat[rho], my_v)) mask |= 1u << rho;
+        smask[tid] = mask;
+        if (j < n_in) {
+            const int i = rsp + j * RS;
+            sbase[tid] = (uint32_t)(((size_t)e_no * pb.in * P * C + (size_t)i * P * slice_cols) >> 3);
+            sval[tid] = my_v;
+        }
+        const int wrows = __reduce_add_sync(0xffffffffu, __popc(mask));
+        if (lane == 0 && wrows) atomicAdd(&hdr.sel_rows, wrows);
+        __syncthreads();
+        V2_TRACE(8);
+
+        const int n_pass = min(NT, n_in - j0);
+        if (!consumer) {
+            // ---- 3a. producer of pair `pair`: the next input nobody has taken, its selected runs into the ring ----
+            const uint32_t ticket_saddr = (uint32_t)__cvta_generic_to_shared(&hdr.ticket);
+            auto fill = [&](uint32_t src16, int len, float val) {  // len rows (0 = stop marker) into the next slot
+                const uint32_t sa = ring_saddr + (uint32_t)slot * kV4SlotBytes;
+                if (filled >= kV4Slots) {  // the slot's previous unit must have been consumed
+                    if (!mbar_wait((uint32_t)__cvta_generic_to_shared(&hdr.empty_bar[pair][slot]), (phase >> slot) & 1u)) {
+                        if (pb.err_flag && lane == 0) atomicExch(pb.err_flag, 3u);
+                    }
+                    phase ^= 1u << slot;
+                }
+                filled++;
+                const int pieces = len * (int)rs16;
+                const uint4* src = bk16 + src16;
+                for (int q = lane; q < pieces; q += 32) cp_async16(sa + (uint32_t)q * 16u, src + q, pol);
+                if (lane == 0)
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sa + (uint32_t)kV4SlotData), "r"(__float_as_uint(val)),
+                                 "r"((uint32_t)len), "r"((uint32_t)seg_bytes), "r"(0u) : "memory");
+                const uint32_t fb = (uint32_t)__cvta_generic_to_shared(&hdr.full_bar[pair][slot]);
+                cp_async_arrive_noinc(fb);  // arrives when this lane's copies have landed
+                __syncwarp();
+                if (lane == 0) mbar_arrive(fb);  // releases the header
+                slot = (slot + 1) & (kV4Slots - 1);
+            };
+#pragma unroll 1
+            for (;;) {
+                uint32_t jj = 0;
+                if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(jj) : "r"(ticket_saddr) : "memory");
+                jj = __shfl_sync(0xffffffffu, jj, 0);
+                if ((int)jj >= n_pass) break;
+                unsigned m = smask[jj];
+                if (!m) continue;
+                const uint32_t sb = sbase[jj];
+                const float sv = sval[jj];
+                while (m) {  // maximal runs of selected ranks: one unit each (a prefix of the ranks in the normal case)
+                    const int st = __ffs((int)m) - 1;
+                    const int len = __ffs((int)~(m >> st)) - 1;
+                    m &= ~(((1u << len) - 1u) << st);
+                    fill(sb + (uint32_t)st * rs16, len, sv);
+                }
+            }
+            fill(0u, 0, 0.f);  // stop marker for the consumer
+        } else {
+            // ---- 3b. consumer ----
+#pragma unroll 1
+            for (;;) {
+                const uint32_t sa = ring_saddr + (uint32_t)slot * kV4SlotBytes;
+                if (!mbar_wait((uint32_t)__cvta_generic_to_shared(&hdr.full_bar[pair][slot]), (phase >> slot) & 1u)) {
+                    if (pb.err_flag && lane == 0) atomicExch(pb.err_flag, 2u);
+                    break;
+                }
+                phase ^= 1u << slot;
+                uint32_t hv, hn, hs, hz;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hv), "=r"(hn), "=r"(hs), "=r"(hz) : "r"(sa + (uint32_t)kV4SlotData));
+                const int n = (int)hn;
+                const uint32_t eb = (uint32_t)__cvta_generic_to_shared(&hdr.empty_bar[pair][slot]);
+                slot = (slot + 1) & (kV4Slots - 1);
+                if (n == 0) {
+                    if (lane == 0) mbar_arrive(eb);
+                    break;
+                }
+                const float val = __uint_as_float(hv);
+                if (full_width) {
+                    uint32_t a0 = sa + (uint32_t)(lane * LB);
+                    int r = 0;
+                    for (; r + 4 <= n; r += 4, a0 += 4 * kRow) accumulate_unit_fp16<VEC, 4, kRow>(base_lane, val, a0);
+                    switch (n - r) {
+                        case 1: accumulate_unit_fp16<VEC, 1, kRow>(base_lane, val, a0); break;
+                        case 2: accumulate_unit_fp16<VEC, 2, kRow>(base_lane, val, a0); break;
+                        case 3: accumulate_unit_fp16<VEC, 3, kRow>(base_lane, val, a0); break;
+                        default: break;
+                    }
+                } else {  // narrow slice: rows are seg_bytes apart, R rows per step, lanes past the slice idle
+                    for (int st = 0; st * R < n; st++) {
+                        const int r = st * R + rowslot;
+                        const bool ok = (rowslot < R) && (r < n) && col_ok;
+                        uint32_t ww[2] = {0u, 0u};
+                        if (ok) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(ww[0]), "=r"(ww[1]) : "r"(sa + (uint32_t)(r * seg_bytes + lcol * LB)));
+                        accumulate_words<SLOTS, VEC>(base_lane, ok ? val : 0.f, ww);
+                    }
+                }
+                __syncwarp();  // every lane has read the unit's bytes
+                if (lane == 0) mbar_arrive(eb);
+            }
+        }
+    }
+    __syncthreads();
+    if (pb.sel_counts && slice == 0 && tid == 0) pb.sel_counts[rsp] = (uint32_t)hdr.sel_rows;
+    V2_TRACE(9);
+
+    // ---- 4. CTA epilogue: sum the 8 consumer tiles and add into out ----
+    {
+        constexpr int NG = NT / TW, SPT = SLOTS / NG;
+        static_assert(SPT == 4, "one 16-byte reduction per thread");
+        const int cl = tid % TW, sg = tid / TW;
+        const int k = cl >> 5, ln = cl & 31;
+        float acc[SPT] = {0.f, 0.f, 0.f, 0.f};
+        const bool col_on = (ln < lpr) && (ln * VEC + k < slice_cols);
+        if (col_on) {
+            for (int rs2 = 0; rs2 < R; rs2++) {
+                const int word0 = (sg * SPT) * TW + k * 32 + ln + rs2 * lpr;
+#pragma unroll
+                for (int w = 0; w < NC; w++)
+#pragma unroll
+                    for (int s = 0; s < SPT; s++) acc[s] += tiles[(size_t)w * TF + word0 + s * TW];
+            }
+        }
+        if (pb.out_mode == kOutOverwrite) {
+            if (tid == 0) {
+                const unsigned* cnt = pb.sync + 2 * slice;
+                const unsigned long long t0 = gtime_ns();
+                while (ld_acquire_u32(cnt) < (unsigned)RS) {
+                    if (gtime_ns() - t0 > 2000000000ull) {
+                        if (pb.err_flag) atomicExch(pb.err_flag, 1u);
+                        break;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (col_on) {
+            const int col = slice * pb.W + ln * VEC + k;
+            red_add_v4(pb.out + (size_t)col * SLOTS + sg * SPT, acc[0], acc[1], acc[2], acc[3]);
+        }
+        if (pb.out_mode == kOutOverwrite) {
+            __syncthreads();
+            if (tid == 0) {
+                unsigned* sy = pb.sync + 2 * slice;
+                const unsigned old = atomicAdd(sy + 1, 1u);
+                if (old == (unsigned)RS - 1u) { sy[0] = 0u; sy[1] = 0u; }
+            }
+        }
+    }
+    V2_TRACE(10);
+}
+
+}  // namespace effort

@@ -15,6 +15,7 @@
 #include "bucket_mul.cuh"
 #include "bucket_mul_v2.cuh"
 #include "bucket_mul_v3.cuh"
+#include "bucket_mul_v4.cuh"
 #include "comm.cuh"
 #include "convert.cuh"
 #include "cutoff.cuh"
@@ -84,8 +85,9 @@ struct effort_ctx {
     unsigned* v2_sync = nullptr;          // [kMaxBatch][kV2MaxSlices][2] arrive/depart counters (overwrite protocol)
     unsigned* v2_err = nullptr;           // [1] set by a kernel whose overwrite barrier timed out
     int cutoff_mode = 0;                  // EFFORT_CUTOFF_SELECT / EFFORT_CUTOFF_BISECT
-    int stage_mode = 2;                   // 2 = TMA pipeline (producer warp + byte ring; slice-major FP16 weights),
-                                          // 0 = per-warp cp.async (LDGSTS) rings, 1 = per-warp cp.async.bulk rings
+    int stage_mode = 3;                   // 3 = consumer/producer warp pairs, whole-input units (slice-major FP16 weights; default)
+                                          // 2 = one TMA producer warp + byte ring (slice-major FP16 weights; measured slower)
+                                          // 0 = per-warp cp.async rings, units of <= 4 rows (any layout, Q4)
     int engine = 2;                       // 2 = bucket_mul_v2_kernel, 1 = round-1 fused kernel + integrate
     int dynamic = 0;                      // v2 per-warp rings: units from a shared counter (1) or static round robin (0, measured faster)
     int last_rs[8] = {0};                 // row splits of the last v2 launch per batch slot (effort_last_selected)
@@ -148,7 +150,7 @@ extern "C" int effort_ctx_create(int device, effort_ctx_t** ctx_out) {
     CK(cudaMemset(c->sel_counts, 0, sizeof(uint32_t) * kMaxBatch * c->n_sms));
     c->sel_cap = (size_t)kMaxBatch * c->n_sms;
     { const char* e = getenv("EFFORT_CUTOFF"); if (e && !strcmp(e, "bisect")) c->cutoff_mode = 1; }
-    { const char* e = getenv("EFFORT_STAGE"); if (e) c->stage_mode = !strcmp(e, "bulk") ? 1 : !strcmp(e, "ldgsts") ? 0 : 2; }
+    { const char* e = getenv("EFFORT_STAGE"); if (e) c->stage_mode = !strcmp(e, "ldgsts") ? 0 : !strcmp(e, "tma") ? 2 : 3; }
     { const char* e = getenv("EFFORT_ENGINE"); if (e && atoi(e) == 1) c->engine = 1; }
     { const char* e = getenv("EFFORT_DYN"); if (e) c->dynamic = atoi(e) ? 1 : 0; }
     if (getenv("EFFORT_TRACE")) {
@@ -168,7 +170,7 @@ extern "C" int effort_ctx_set_cutoff_mode(effort_ctx_t* c, int mode) {
 extern "C" int effort_ctx_set_option(effort_ctx_t* c, const char* name, int value) {
     if (!c || !name) return EFFORT_EINVAL;
     if (!strcmp(name, "engine")) { if (value != 1 && value != 2) return EFFORT_EINVAL; c->engine = value; return EFFORT_OK; }
-    if (!strcmp(name, "stage")) { if (value < 0 || value > 2) return EFFORT_EINVAL; c->stage_mode = value; return EFFORT_OK; }
+    if (!strcmp(name, "stage")) { if (value != 0 && value != 2 && value != 3) return EFFORT_EINVAL; c->stage_mode = value; return EFFORT_OK; }
     if (!strcmp(name, "dynamic")) { if (value != 0 && value != 1) return EFFORT_EINVAL; c->dynamic = value; return EFFORT_OK; }
     return EFFORT_EINVAL;
 }
@@ -519,9 +521,7 @@ static int launch_v2_batch(effort_ctx* ctx, const V2Call* calls, int n, int slot
     batch.cta_begin[n] = cta;
     batch.list_cap = (list_cap + 63) & ~63;
     using L = V2Smem<SLOTS, VEC>;
-    bool bulk = ctx->stage_mode == 1;  // per-warp bulk rings (experiment)
-    // one bulk copy per unit needs the unit's rows contiguous in HBM: the slice-major device layout
-    for (int k = 0; k < n; k++) bulk = bulk && calls[k].w->layout == kSliceMajor;
+    const bool bulk = false;  // the per-warp cp.async.bulk rings of the first round-2 draft lost to cp.async and are not offered
     batch.dynamic = ctx->dynamic;
     const size_t smem = L::bytes(batch.list_cap, D);
     if (smem > kMaxSmem) return EFFORT_ESHAPE;
@@ -541,7 +541,10 @@ static int launch_v2_batch(effort_ctx* ctx, const V2Call* calls, int n, int slot
     const bool bisect = ctx->cutoff_mode == 1;
     bool all_slice = true;
     for (int k = 0; k < n; k++) all_slice = all_slice && calls[k].w->layout == kSliceMajor;
-    if (SLOTS == 16 && all_slice && ctx->stage_mode == 2) {
+    if (SLOTS == 16 && all_slice && ctx->stage_mode == 3) {
+        // consumer / producer warp pairs with private rings (bucket_mul_v4.cuh): the default path
+        rc = bisect ? go(bucket_mul_v4_kernel<kCutBisect>, kV2Threads, V4Smem::kBytes) : go(bucket_mul_v4_kernel<kCutSelect>, kV2Threads, V4Smem::kBytes);
+    } else if (SLOTS == 16 && all_slice && ctx->stage_mode == 2) {
         // TMA pipeline: producer warp + byte ring (bucket_mul_v3.cuh)
         batch.ring_bytes = (int)((kMaxSmem - V3Smem::kFixed) & ~(size_t)255);
         if (batch.ring_bytes < 2 * (kV3BatchBytes + 4096)) return EFFORT_ESHAPE;
@@ -1095,6 +1098,14 @@ static int comm_all_reduce_site(effort_ctx* ctx, int site, float* buf, size_t co
 static int comm_all_gather_site(effort_ctx* ctx, int site, const float* send, float* recv, size_t count, cudaStream_t s) {
     if (ctx->comm_world > 1 && ctx->p2p_ready && p2p_enabled()) return p2p_launch<0>(ctx, site, send, recv, count, s);
     return effort_comm_all_gather(ctx, send, recv, count, s);
+}
+
+extern "C" int effort_comm_p2p_collective(effort_ctx_t* ctx, int mode, int site, const float* send_dev, float* out_dev,
+                                          size_t count, void* stream) {
+    if (!ctx || !send_dev || !out_dev || (mode != 0 && mode != 1)) return EFFORT_EINVAL;
+    if (!ctx->p2p_ready || ctx->comm_world < 2) return EFFORT_ESTATE;
+    return mode == 0 ? p2p_launch<0>(ctx, site, send_dev, out_dev, count, (cudaStream_t)stream)
+                     : p2p_launch<1>(ctx, site, send_dev, out_dev, count, (cudaStream_t)stream);
 }
 
 extern "C" int effort_comm_all_reduce(effort_ctx_t* ctx, float* buf_dev, size_t count, void* stream) {

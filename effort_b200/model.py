@@ -111,16 +111,20 @@ class DecodeModel:
     @classmethod
     def random_init(cls, cfg: MistralConfig = MistralConfig(), seed: int = 1234, keep_reference_layout: bool = False,
                     ctx: Optional[ops.Context] = None, norm_jitter: float = 0.1, tp_rank: int = 0,
-                    tp_size: int = 1, weight_flags: int = 0, weight_fn=None) -> "DecodeModel":
+                    tp_size: int = 1, weight_flags: int = 0, weight_fn=None, keep_dense: bool = False) -> "DecodeModel":
         """Random-init weights ~ N(0, 0.02^2), converted on the GPU (effort_bucketize).
         With tp_size > 1 every rank draws the SAME full matrices (same seed), converts them and keeps its shard
         (effort_b200/sharding.py): the sharded model computes what the unsharded one does."""
         m = cls(cfg, ctx, tp_rank, tp_size)
         gen = torch.Generator(device="cuda").manual_seed(seed)
         kvd = cfg.n_kv_heads * cfg.head_dim
+        m.dense = [] if keep_dense else None    # keep_dense: the dense fp16 [out,in] matrices per layer (quality baseline)
+        cur = []
 
         def make(out_dim, in_dim, mode="column"):
             w = (weight_fn or _rand_w)(out_dim, in_dim, gen)
+            if keep_dense:
+                cur.append(w)
             t = ops.bucketize(w)
             if tp_size > 1:
                 fn = sharding.shard_columns if mode == "column" else sharding.shard_rows
@@ -138,6 +142,9 @@ class DecodeModel:
             m.set_layer(i, make(cfg.dim, cfg.dim), make(kvd, cfg.dim), make(kvd, cfg.dim), make(cfg.dim, cfg.dim, "row"),
                         make(cfg.hidden_dim, cfg.dim), make(cfg.dim, cfg.hidden_dim, "row"),
                         make(cfg.hidden_dim, cfg.dim), norm_vec(), norm_vec())
+            if keep_dense:
+                m.dense.append(list(cur))
+                cur.clear()
         out_core = _rand_w(cfg.vocab, cfg.dim, gen)
         if tp_size > 1:
             v0, v1 = cfg.vocab * tp_rank // tp_size, cfg.vocab * (tp_rank + 1) // tp_size

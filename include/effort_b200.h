@@ -86,9 +86,11 @@ int effort_ctx_set_cutoff_mode(effort_ctx_t* ctx, int mode);
 /* Tuning / A-B knobs of the fused operator (tests and tools; every value computes the same operator):
  *   "engine"   2 (default) round-2 kernel: one launch per group, staged streaming, reductions into `out`;
  *              1 round-1 kernel + integrate launch (deterministic fp32 order)
- *   "stage"    2 (default) TMA pipeline: a producer warp issues one cp.async.bulk per streaming unit into a shared byte
- *              ring, 16 consumer warps accumulate (slice-major FP16 weights; other weights take stage 0);
- *              0 per-warp cp.async rings; 1 per-warp cp.async.bulk rings (slice-major weights)
+ *   "stage"    3 (default) eight consumer warps accumulate, eight producer warps stage whole-input units (1..16 rows)
+ *              with cp.async into per-pair rings and hand them over through mbarriers (slice-major FP16 weights; other
+ *              weights take stage 0); 2 one TMA (cp.async.bulk) producer warp, a shared byte ring and 16 consumers
+ *              (slice-major FP16 weights; measured slower: the single producer's serial issue is the limit);
+ *              0 sixteen self-serving warps with private cp.async rings, units of at most 4 rows
  *   "dynamic"  per-warp rings (stage 0/1) only: 0 (default) static round robin of the units, 1 units from a shared counter
  * Returns EFFORT_EINVAL for an unknown name or value.  Environment defaults: EFFORT_ENGINE, EFFORT_STAGE=bulk,
  * EFFORT_DYN. */
@@ -203,6 +205,12 @@ int effort_comm_destroy(effort_ctx_t* ctx);
  * returns its 64-byte cudaIpcMemHandle_t; connect: takes all ranks' handles (world x 64 bytes, rank order). */
 int effort_comm_p2p_local_handle(effort_ctx_t* ctx, void* handle64_out);
 int effort_comm_p2p_connect(effort_ctx_t* ctx, const void* handles, int rank, int world);
+/* Test hook for the one-shot NVLink collectives themselves (the decode loop calls them internally): mode 0 = all-gather
+ * (send: count floats, out: world*count floats in rank order), mode 1 = all-reduce (out: count floats, summed in rank
+ * order); `site` (0..15) names the call position -- every rank must use the same sequence of sites, and a site may be
+ * reused only after a later site's collective.  EFFORT_ESTATE unless effort_comm_p2p_connect succeeded. */
+int effort_comm_p2p_collective(effort_ctx_t* ctx, int mode, int site, const float* send_dev, float* out_dev, size_t count,
+                               void* stream);
 /* back to NCCL for the exchanges (call on EVERY rank when any rank failed to connect: the choice must be collective) */
 int effort_comm_p2p_disable(effort_ctx_t* ctx);
 /* in-place sum all-reduce / all-gather of fp32 device buffers over the ctx communicator (test + building block) */

@@ -256,11 +256,11 @@ def test_no_repack_layout_same_selection_and_sum(T, ops):
 
 
 @pytest.mark.parametrize("in_dim,out_dim", [(4096, 4096), (4096, 1024), (4096, 11008), (14336, 4096)])
-@pytest.mark.parametrize("stage,flags", [(0, 2), (1, 2), (2, 2), (0, 4), (2, 4)])
+@pytest.mark.parametrize("stage,flags", [(0, 2), (2, 2), (3, 2), (0, 4), (3, 4)])
 def test_layouts_and_bulk_stage(T, ops, mode, in_dim, out_dim, stage, flags):
     """device layouts (2 = slice-major: contiguous row sets per column slice, the default; 4 = input-major) x staging
-    (2 = TMA pipeline with a producer warp, the default; 0 = per-warp cp.async rings; 1 = per-warp cp.async.bulk rings):
-    every combination computes the same operator (input-major weights always take the cp.async rings)"""
+    (3 = consumer/producer warp pairs, the default; 2 = one TMA producer warp + byte ring; 0 = self-serving warps with
+    private cp.async rings): every combination computes the same operator (input-major weights always take stage 0)"""
     w, r = conv(out_dim, in_dim)
     v = make_v(in_dim, 5)
     ctx = ops.default_context()
@@ -274,7 +274,7 @@ def test_layouts_and_bulk_stage(T, ops, mode, in_dim, out_dim, stage, flags):
             assert ops.lastSelected() == res["n_selected"]
             assert rel_err(out.cpu().numpy(), res["out64"]) <= OUT_TOL
     finally:
-        ctx.setOption("stage", 2)
+        ctx.setOption("stage", 3)
 
 
 @pytest.mark.parametrize("opt,val", [("dynamic", 1), ("engine", 1)])
@@ -297,7 +297,7 @@ def test_engine_options_same_result(T, ops, opt, val):
         assert rel_err(out.cpu().numpy(), res["out64"]) <= OUT_TOL
     finally:
         ctx.setOption(opt, 0 if opt == "dynamic" else 2)
-        ctx.setOption("stage", 2)
+        ctx.setOption("stage", 3)
 
 
 def test_expert_number_selects_expert(T, ops, mode):

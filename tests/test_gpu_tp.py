@@ -1,0 +1,133 @@
+"""Tensor parallel on real devices (needs >= 2 GPUs on the box; skipped otherwise): the one-shot NVLink collectives of
+csrc/comm.cuh under CUDA-graph replay against host-computed results, and the sharded decode loop against the unsharded
+model.  One process per GPU (torch.multiprocessing spawn, NCCL rendezvous on 127.0.0.1)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _init(rank, world, port):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    from effort_b200 import ops
+    from effort_b200.model import init_comm
+    ctx = ops.default_context()
+    init_comm(ctx, rank, world)
+    return torch, dist, ops, ctx
+
+
+def _collectives_worker(rank, world, port, replays):
+    torch, dist, ops, ctx = _init(rank, world, port)
+    import ctypes as C
+    from effort_b200 import _lib
+    L = _lib.load()
+    n_g, n_r = 1792, 4096                       # the decode loop's sizes at 8 ranks: x2 slice gather, out all-reduce
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        send = torch.arange(n_g, dtype=torch.float32, device="cuda") * 0.5 + rank
+        gathered = torch.zeros(world * n_g, dtype=torch.float32, device="cuda")
+        part = torch.linspace(-1, 1, n_r, device="cuda") * (rank + 1)
+        red = torch.zeros(n_r, dtype=torch.float32, device="cuda")
+
+        def enqueue():
+            send.add_(float(rank + 1))
+            part.mul_(1.0009765625)                 # exact in fp32 for a while: keeps the expected value computable
+            sp = torch.cuda.current_stream().cuda_stream
+            _lib.check(L.effort_comm_p2p_collective(ctx._h, 0, 5, send.data_ptr(), gathered.data_ptr(), n_g, sp), "all-gather")
+            _lib.check(L.effort_comm_p2p_collective(ctx._h, 1, 6, part.data_ptr(), red.data_ptr(), n_r, sp), "all-reduce")
+
+        enqueue()                                    # eager once
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            enqueue()
+        done = 2
+        for k in range(replays):
+            g.replay()
+            done += 1
+            if k % 97 == 0 or k == replays - 1:
+                torch.cuda.synchronize()
+                got = gathered.cpu().numpy().reshape(world, n_g)
+                for r in range(world):
+                    want = np.arange(n_g, dtype=np.float32) * np.float32(0.5) + np.float32(r)
+                    for _ in range(done):
+                        want = want + np.float32(r + 1)
+                    assert np.array_equal(got[r], want), (rank, r, k)
+                want = np.zeros(n_r, np.float32)
+                for r in range(world):                # summed in rank order on every rank
+                    x = (np.linspace(-1, 1, n_r, dtype=np.float64).astype(np.float32) * np.float32(r + 1))
+                    for _ in range(done):
+                        x = x * np.float32(1.0009765625)
+                    want = want + x
+                # linspace on the device vs numpy may differ in the last bit: compare with a tight tolerance instead
+                assert np.allclose(red.cpu().numpy(), want, rtol=2e-6, atol=1e-6), (rank, k)
+        assert ctx.errorFlag() == 0
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _decode_worker(rank, world, port):
+    torch, dist, ops, ctx = _init(rank, world, port)
+    from effort_b200.model import DecodeModel, MistralConfig
+    cfg = MistralConfig(n_layers=2, vocab=4096, max_seq=64)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        tp = DecodeModel.random_init(cfg, seed=7, tp_rank=rank, tp_size=world)
+        ref = DecodeModel.random_init(cfg, seed=7, ctx=ops.Context()) if rank == 0 else None
+        for use_graph in (False, True):
+            tp.set_graphs(use_graph)
+            tp.reset()
+            if rank == 0:
+                ref.reset()
+            for t in (1, 17, 400, 999):
+                tok = torch.tensor([t], dtype=torch.int32, device="cuda")
+                tp.step(tok, 0.5)
+                torch.cuda.synchronize()
+                if rank == 0:
+                    ref.step(tok, 0.5)
+                    torch.cuda.synchronize()
+                    a, b = tp.logits().double(), ref.logits().double()
+                    cs = float((a @ b) / (a.norm() * b.norm()))
+                    assert cs > 0.999, (world, use_graph, t, cs)
+                dist.barrier()
+        assert ctx.errorFlag() == 0
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_p2p_collectives_under_graph_replay(world):
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_collectives_worker, args=(world, _free_port(), 1000), nprocs=world, join=True)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_decode_matches_unsharded(world):
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_decode_worker, args=(world, _free_port()), nprocs=world, join=True)

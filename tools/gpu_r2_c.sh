@@ -1,0 +1,19 @@
+#!/bin/bash
+# round 2, GPU call C: consumer/producer pair kernel (bucket_mul_v4)
+mkdir -p gpurun_out
+O=gpurun_out
+rm -f $O/r2c_rc.txt
+timeout 120 python tools/prof_one.py --shape 4096x14336 --effort 0.25 --n 4 > $O/r2c_first.log 2>&1; echo "first rc=$?" >> $O/r2c_rc.txt
+timeout 900 python -m pytest tests/test_gpu_parity.py -q --maxfail=10 > $O/r2c_parity.log 2>&1; echo "parity rc=$?" >> $O/r2c_rc.txt
+timeout 600 python -m pytest tests/test_gpu_decode.py -q --maxfail=10 -k "not 32_layers" > $O/r2c_decode.log 2>&1; echo "decode rc=$?" >> $O/r2c_rc.txt
+SW="--shapes 4096x14336,4096x4096,14336x4096,4096x1024 --efforts 1.0,0.5,0.25 --iters 30 --reps 20 --warm_s 0.3"
+timeout 300 python tools/sweep.py $SW --out $O/r2c_sweep_v4.json > $O/r2c_sweep_v4.log 2>&1
+EFFORT_STAGE=ldgsts timeout 300 python tools/sweep.py $SW --out $O/r2c_sweep_ldgsts.json > $O/r2c_sweep_ldgsts.log 2>&1
+EFFORT_CUTOFF=bisect timeout 300 python tools/sweep.py $SW --out $O/r2c_sweep_bisect.json > $O/r2c_sweep_bisect.log 2>&1
+timeout 200 python tools/trace_v2.py --shape 4096x14336 --effort 0.25 > $O/r2c_trace_025.txt 2>&1
+timeout 200 python tools/trace_v2.py --shape 4096x14336 --effort 1.0 > $O/r2c_trace_100.txt 2>&1
+timeout 200 python tools/trace_v2.py --shape 4096x4096 --effort 0.25 > $O/r2c_trace_wq_025.txt 2>&1
+timeout 900 python bench.py --steps 32 --warmup 8 > $O/r2c_bench.json 2> $O/r2c_bench.err; echo "bench rc=$?" >> $O/r2c_rc.txt
+cat $O/r2c_rc.txt
+tail -n 3 $O/r2c_parity.log $O/r2c_decode.log
+tail -n 12 $O/r2c_sweep_v4.log
