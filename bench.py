@@ -55,15 +55,15 @@ def cpu_layer_sample(effort: float, reps: int = 5, seed: int = 1234):
     """One transformer layer's 7 GEMVs on the host cores (oracle port, OpenMP, the reference's bisection cutoff).
     Returns seconds per layer for the bucketMul port at `effort` and for the dense fp16 GEMV (basicMul,
     matrix.metal:150-162 -- the dense CPU baseline north_star asks for): MEDIAN of `reps` repetitions after one warm-up,
-    min/max reported.  The thread count is fixed once: every CPU the process may run on (sched_getaffinity), threads
-    bound to cores (OMP_PROC_BIND / OMP_PLACES, set before the OpenMP runtime starts)."""
-    os.environ.setdefault("OMP_PROC_BIND", "close")
-    os.environ.setdefault("OMP_PLACES", "cores")
+    min/max reported.  Thread count: the boxes expose 64-128 logical CPUs but SMT / cgroup quotas make "all of them"
+    slower than fewer, so the count is chosen ONCE among {all, 1/2, 1/4} of the CPUs the process may run on by the median
+    of three dense 4096->14336 GEMVs each (round 1 picked it from a single timed probe and landed on a 12x slower count
+    on one box), then stays fixed and is reported as `cores`.  (Binding threads with OMP_PROC_BIND was tried: 400x slower
+    inside these containers.)"""
     import numpy as np
     from oracle import oracle as O
     from tests.util import make_v, make_w
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    O.set_threads(avail)
     O.set_cutoff_mode("bisect")
     by_shape, dense = {}, {}
     for k, (i, o) in enumerate(sorted(set(SHAPES_PER_LAYER))):
@@ -83,7 +83,21 @@ def cpu_layer_sample(effort: float, reps: int = 5, seed: int = 1234):
         for (i, o) in SHAPES_PER_LAYER:
             O.basic_mul_fast(vs[i], dense[(i, o)], outs[o])
 
-    res = {"threads": O.num_threads(), "reps": reps}
+    best_t, best_dt = 1, float("inf")
+    probe_w, probe_out = dense[(4096, 14336)], outs[14336]
+    for nt in sorted({avail, max(1, avail // 2), max(1, avail // 4)}, reverse=True):
+        O.set_threads(nt)
+        O.basic_mul_fast(vs[4096], probe_w, probe_out)   # warm this thread count
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            O.basic_mul_fast(vs[4096], probe_w, probe_out)
+            ts.append(time.perf_counter() - t0)
+        dt = sorted(ts)[1]
+        if dt < best_dt:
+            best_t, best_dt = nt, dt
+    O.set_threads(best_t)
+    res = {"threads": O.num_threads(), "reps": reps, "cpus_available": avail}
     for name, fn in (("bucketmul", run_bucket), ("dense", run_dense)):
         fn()  # warm-up (page faults, thread pool)
         ts = []
@@ -400,10 +414,32 @@ def run_ours(args, rank, local_rank, world):
         quality = q4 = sweep = None
         if want_quality:
             def q_headline():
-                return decode_quality(lambda: model, dense_twin, args.effort, min(args.steps, 16))
-            quality = {"what": "per-token logit cos-sim, effort-e decode vs dense fp16 decode (basicMul on core) of the same tokens",
-                       "effort": args.effort,
+                return {str(e): decode_quality(lambda: model, dense_twin, e, min(args.steps, 8)) for e in (1.0, 0.5, args.effort)}
+            quality = {"what": "per-token logit cos-sim, effort-e decode vs a dense fp16 decode (every projection through basicMul "
+                               "on its core) of the same tokens, all 32 layers.  NOTE: a random-init network has no trained "
+                               "redundancy -- the per-GEMV approximation error (see per_operator) compounds through 224 GEMVs; "
+                               "the reference's >= 0.99 figure is for trained Mistral weights (docs/ryc), which are not available "
+                               "offline",
                        "gaussian N(0, 0.02^2) (headline weights)": guarded(q_headline)}
+
+            def q_per_op():
+                # one layer's seven operators on heavy-tailed activations (tests/util.make_v): bucketMul vs basicMul
+                from tests.util import make_v
+                import numpy as _np
+                from oracle import oracle as O
+                rows = {}
+                for name, w_e, w_d in zip(("wq", "wk", "wv", "wo", "w1", "w2", "w3"), model.layers[0][:7], model.dense[0]):
+                    v = torch.from_numpy(make_v(w_e.inSize, 42)).cuda()
+                    out = torch.empty(w_e.outSize, dtype=torch.float32, device="cuda")
+                    ref = torch.empty_like(out)
+                    ops.basicMul(v, w_d, ref)
+                    r = {}
+                    for e in (1.0, 0.5, args.effort):
+                        ops.bucketMul(v, w_e, None, out, e)
+                        r[str(e)] = round(O.cossim(out.cpu().numpy(), ref.cpu().numpy()), 5)
+                    rows[name] = r
+                return rows
+            quality["per_operator (layer 0, cos-sim of bucketMul vs dense basicMul)"] = guarded(q_per_op)
             model.dense = None
             torch.cuda.empty_cache()
 
@@ -415,7 +451,7 @@ def run_ours(args, rank, local_rank, world):
 
             def q_heavy():
                 hm = DecodeModel.random_init(cfg, seed=77, keep_dense=True, weight_fn=student_t_w(3.0))
-                r = {e: decode_quality(lambda: hm, dense_twin, e, min(args.steps, 16)) for e in (args.effort, 0.5)}
+                r = {str(e): decode_quality(lambda: hm, dense_twin, e, min(args.steps, 8)) for e in (1.0, 0.5, args.effort)}
                 del hm
                 torch.cuda.empty_cache()
                 return r
