@@ -55,6 +55,7 @@ SIGNATURES = {
     "effort_model_create": (C.c_int, [vp, vp, C.POINTER(C.c_void_p)]),
     "effort_model_destroy": (C.c_int, [vp]),
     "effort_model_set_layer": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "effort_model_set_moe": (C.c_int, [vp, C.c_int, vp, C.c_int]),
     "effort_model_set_head": (C.c_int, [vp, vp, vp, vp]),
     "effort_model_reset": (C.c_int, [vp, vp]),
     "effort_model_step": (C.c_int, [vp, vp, C.c_double, vp]),

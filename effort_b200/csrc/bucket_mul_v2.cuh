@@ -55,6 +55,7 @@ struct V2Problem {
     const __half* probes;    // [E][4096]
     const uint32_t* exp_no;  // device scalar or null
     float* out;              // [C * SLOTS]
+    const float* out_scale;  // optional device scalar g: out (+)= g * (W v)  (MoE gate value, runNetwork.swift:196)
     unsigned* sync;          // [CS][2] arrive / depart counters of the overwrite protocol (zero between launches)
     uint32_t* sel_counts;    // [RS] rows selected per row split (written by slice 0)
     float* cutoff_out;       // CTA 0 of the problem stores the cutoff
@@ -484,7 +485,7 @@ bucket_mul_v2_kernel(const __grid_constant__ V2Batch batch) {
             else if (pb.layout == kRankMajor) el0 = ((size_t)e_no * P * pb.in + i) * C;
             else el0 = (size_t)e_no * pb.in * P * C + (size_t)i * P * slice_cols;
             sbase[tid] = (uint32_t)(el0 >> 3);
-            sval[tid] = my_v;
+            sval[tid] = pb.out_scale ? my_v * *pb.out_scale : my_v;  // the selection above used the unscaled input
             if constexpr (SLOTS != 16) {
 #pragma unroll
                 for (int rho = 0; rho < 8; rho++) sstat[tid * 8 + rho] = sel_stat[rho];

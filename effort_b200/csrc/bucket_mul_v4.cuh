@@ -355,7 +355,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
         if (j < n_in) {
             const int i = rsp + j * RS;
             sbase[tid] = (uint32_t)(((size_t)e_no * pb.in * P * C + (size_t)i * P * slice_cols) >> 3);
-            sval[tid] = my_v;
+            sval[tid] = pb.out_scale ? my_v * *pb.out_scale : my_v;  // the selection above used the unscaled input
         }
         const int wrows = __reduce_add_sync(0xffffffffu, __popc(mask));
         if (lane == 0 && wrows) atomicAdd(&hdr.sel_rows, wrows);

@@ -209,6 +209,52 @@ argmax_advance_kernel(const float* __restrict__ logits, int n, int* __restrict__
     }
 }
 
+// ---- MoE routing (runNetwork.swift:185-189): gateOut = basicMul(fxn, ffnGate) with fxn = rmsNormFast(h) * ffn_norm (v cast
+// to fp16 first, helpers/mps.swift:19), the two largest gate logits (mpsTopK, helpers/mps.swift:49-80; ties: lower expert
+// index first -- MPS is closed, unpinned) and gateVals.softmax() = exp(x) / sum(exp(x)) (aux.metal:185-199).  One CTA, one
+// warp per expert (n_experts <= 8 per pass).  The indices stay on the device: the expert GEMVs read them as `expNo`.
+__global__ void __launch_bounds__(256)
+moe_gate_kernel(const float* __restrict__ h, const __half* __restrict__ norm_w, float eps, const __half* __restrict__ gate,
+                int n_experts, int dim, uint32_t* __restrict__ gate_idx, float* __restrict__ gate_val) {
+    __shared__ float red[8];
+    __shared__ float logit[64];
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) { const float x = h[i]; ss += x * x; }
+    ss = warp_sum_f(ss);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    float t = (lane < 8) ? red[lane] : 0.f;
+    t = warp_sum_f(t);
+    const float denom = sqrtf(t / (float)dim + eps);
+    for (int e = warp; e < n_experts && e < 64; e += 8) {
+        const __half* row = gate + (size_t)e * dim;
+        float acc = 0.f;
+        for (int i = lane; i < dim; i += 32) {
+            const float x = __half2float(__float2half_rn((h[i] / denom) * __half2float(norm_w[i])));
+            acc = fmaf(x, __half2float(row[i]), acc);
+        }
+        acc = warp_sum_f(acc);
+        if (lane == 0) logit[e] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int i0 = 0, i1 = -1;
+        for (int e = 1; e < n_experts && e < 64; e++)
+            if (logit[e] > logit[i0]) i0 = e;
+        for (int e = 0; e < n_experts && e < 64; e++)
+            if (e != i0 && (i1 < 0 || logit[e] > logit[i1])) i1 = e;
+        if (i1 < 0) i1 = i0;
+        const float e0 = expf(logit[i0]), e1 = expf(logit[i1]);
+        gate_idx[0] = (uint32_t)i0;
+        gate_idx[1] = (uint32_t)i1;
+        gate_val[0] = e0 / (e0 + e1);
+        gate_val[1] = e1 / (e0 + e1);
+    }
+}
+
 // ---- fused head: final rmsNorm * w on load, dense lm_head GEMV (basicMul, helpers/mps.swift:14-47), greedy argmax ----
 // (runNetwork.swift:206-209 + mpsTopK index 0, :235-257).  One warp per vocabulary row; every CTA keeps its best
 // (logit, index) and the last CTA to finish (atomic ticket) reduces the per-CTA candidates -- lowest index wins ties, the

@@ -454,6 +454,7 @@ struct V2Call {  // one problem of a launch group, host side
     float norm_eps = 1e-5f;
     const effort_weights* w = nullptr;
     const uint32_t* exp_no = nullptr;
+    const float* out_scale = nullptr;  // device scalar: out (+)= scale * (W v)
     float* out = nullptr;
     double effort = 0.25;
     int out_mode = kOutOverwrite;
@@ -501,7 +502,7 @@ static int launch_v2_batch(effort_ctx* ctx, const V2Call* calls, int n, int slot
         if (!c.v_cut && w->in < EFFORT_PROBES_MAX) return EFFORT_ESHAPE;
         pb.v = c.v; pb.v2 = c.v2; pb.v_cut = c.v_cut ? c.v_cut : c.v; pb.norm_w = c.norm_w; pb.norm_eps = c.norm_eps;
         pb.st16 = w->st16; pb.st32 = w->st32; pb.bk = w->fast_bk(); pb.probes = w->probes; pb.exp_no = c.exp_no;
-        pb.out = c.out;
+        pb.out = c.out; pb.out_scale = c.out_scale;
         pb.sync = ctx->v2_sync + (size_t)(slot0 + k) * kV2MaxSlices * 2;
         pb.sel_counts = ctx->sel_counts + (size_t)(slot0 + k) * ctx->n_sms;
         pb.cutoff_out = ctx->cutoff + slot0 + k;
@@ -1144,6 +1145,8 @@ struct effort_model {
                              *w3 = nullptr;
         const __half *attn_norm = nullptr, *ffn_norm = nullptr;
         float *kc = nullptr, *vc = nullptr;
+        const __half* gate = nullptr;  // MoE: [n_experts, dim] fp16 (layers.N.feed_forward.gate, loader.swift:208-212)
+        int n_experts = 1;
     };
     std::vector<Layer> layers;
     const __half *norm = nullptr, *out_core = nullptr, *emb = nullptr;
@@ -1159,6 +1162,8 @@ struct effort_model {
     // the chain has cleared (layer parity picks the buffer)
     float *xq2[2] = {nullptr, nullptr}, *xk2[2] = {nullptr, nullptr}, *xv2[2] = {nullptr, nullptr};
     float *x1_2[2] = {nullptr, nullptr}, *x3_2[2] = {nullptr, nullptr};
+    uint32_t* gate_idx = nullptr;  // MoE: the two routed experts of the current layer (device, read as expNo)
+    float* gate_val = nullptr;     // MoE: their softmax weights
     float2* head_cand = nullptr;   // per-CTA argmax candidates of head_kernel
     unsigned* head_ticket = nullptr;
     int host_pos = 0;              // tokens decoded since the last reset (bounds the KV cache)
@@ -1223,7 +1228,9 @@ extern "C" int effort_model_create(effort_ctx_t* ctx, const effort_model_config_
             (rc = model_alloc(m, m->x3_2[b], cfg->hidden_dim)))
             return rc;
     }
-    if ((rc = model_alloc(m, m->head_cand, (size_t)ctx->n_sms * 8)) || (rc = model_alloc(m, m->head_ticket, 1))) return rc;
+    if ((rc = model_alloc(m, m->head_cand, (size_t)ctx->n_sms * 8)) || (rc = model_alloc(m, m->head_ticket, 1)) ||
+        (rc = model_alloc(m, m->gate_idx, 2)) || (rc = model_alloc(m, m->gate_val, 2)))
+        return rc;
     CK(cudaMallocHost(&m->h_token, sizeof(int)));
     CK(cudaMallocHost(&m->h_next, sizeof(int)));
     CK(cudaMallocHost(&m->h_logits, sizeof(float) * cfg->vocab));
@@ -1257,6 +1264,17 @@ extern "C" int effort_model_set_layer(effort_model_t* m, int layer, const effort
     auto& l = m->layers[layer];
     l.wq = wq; l.wk = wk; l.wv = wv; l.wo = wo; l.w1 = w1; l.w2 = w2; l.w3 = w3;
     l.attn_norm = (const __half*)attn_norm_dev; l.ffn_norm = (const __half*)ffn_norm_dev;
+    for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
+    m->graphs.clear();
+    return EFFORT_OK;
+}
+
+extern "C" int effort_model_set_moe(effort_model_t* m, int layer, const void* gate_dev, int n_experts) {
+    if (!m || layer < 0 || layer >= m->cfg.n_layers || !gate_dev || n_experts < 2 || n_experts > 64) return EFFORT_EINVAL;
+    auto& l = m->layers[layer];
+    if (!l.w1 || l.w1->n_experts != n_experts || l.w2->n_experts != n_experts || l.w3->n_experts != n_experts) return EFFORT_ESHAPE;
+    l.gate = (const __half*)gate_dev;
+    l.n_experts = n_experts;
     for (auto& g : m->graphs) cudaGraphExecDestroy(g.second);
     m->graphs.clear();
     return EFFORT_OK;
@@ -1383,17 +1401,30 @@ static int model_enqueue_token_v2(effort_model* m, double effort, cudaStream_t s
         V2Call wo;
         wo.v = m->attn; wo.w = l.wo; wo.out = m->h; wo.effort = effort; wo.out_mode = kOutAccumulate;
         if ((rc = launch_v2(ctx, &wo, 1, 0, s))) return rc;
-        V2Call w13[2];
-        const effort_weights* ww[2] = {l.w1, l.w3};
-        float* o13[2] = {m->x1_2[b], m->x3_2[b]};
-        for (int k = 0; k < 2; k++) {
-            w13[k].v = m->h; w13[k].norm_w = l.ffn_norm; w13[k].norm_eps = c.norm_eps; w13[k].w = ww[k];
-            w13[k].out = o13[k]; w13[k].effort = effort; w13[k].out_mode = kOutAccumulate;
+        const int n_routed = l.gate ? 2 : 1;  // MoE: the two experts the gate picks (runNetwork.swift:185-200)
+        if (l.gate) {
+            CK(launch_pdl(moe_gate_kernel, dim3(1), dim3(256), 0, s, (const float*)m->h, l.ffn_norm, c.norm_eps, l.gate, l.n_experts,
+                          c.dim, m->gate_idx, m->gate_val));
+            LAUNCHED();
         }
-        if ((rc = launch_v2(ctx, w13, 2, 0, s))) return rc;
-        V2Call w2;
-        w2.v = m->x1_2[b]; w2.v2 = m->x3_2[b]; w2.w = l.w2; w2.out = m->h; w2.effort = effort; w2.out_mode = kOutAccumulate;
-        if ((rc = launch_v2(ctx, &w2, 1, 0, s))) return rc;
+        for (int r = 0; r < n_routed; r++) {
+            V2Call w13[2];
+            const effort_weights* ww[2] = {l.w1, l.w3};
+            float* o13[2] = {m->x1_2[b], m->x3_2[b]};
+            for (int k = 0; k < 2; k++) {
+                w13[k].v = m->h; w13[k].norm_w = l.ffn_norm; w13[k].norm_eps = c.norm_eps; w13[k].w = ww[k];
+                w13[k].out = o13[k]; w13[k].effort = effort;
+                // dense layers accumulate into buffers an earlier kernel cleared; a routed expert overwrites (the second
+                // expert reuses the buffers of the first)
+                w13[k].out_mode = l.gate ? kOutOverwrite : kOutAccumulate;
+                w13[k].exp_no = l.gate ? m->gate_idx + r : nullptr;
+            }
+            if ((rc = launch_v2(ctx, w13, 2, 0, s))) return rc;
+            V2Call w2;
+            w2.v = m->x1_2[b]; w2.v2 = m->x3_2[b]; w2.w = l.w2; w2.out = m->h; w2.effort = effort; w2.out_mode = kOutAccumulate;
+            if (l.gate) { w2.exp_no = m->gate_idx + r; w2.out_scale = m->gate_val + r; }  // h += gateVal * ffnOut (:196-199)
+            if ((rc = launch_v2(ctx, &w2, 1, 0, s))) return rc;
+        }
     }
     return enqueue_head(m, m->h, m->norm, m->out_core, c.vocab, 0, m->logits, true, s);
 }
@@ -1410,6 +1441,8 @@ static int model_enqueue_token(effort_model* m, double effort, cudaStream_t s) {
     int rc;
     const bool v2_chain = G == 1 && m->chain == 2 && ctx->engine == 2 && model_all_fp16_v2(m);
     if (v2_chain) return model_enqueue_token_v2(m, effort, s);
+    for (const auto& l : m->layers)
+        if (l.gate) return EFFORT_ESTATE;  // expert routing lives in the fused chain only
     CK(launch_pdl(embed_kernel, dim3(4), dim3(1024), 0, s, (const int*)m->token, m->emb, c.dim, c.vocab, m->h, m->sumsq_a,
                   ZeroList{}));
     LAUNCHED();

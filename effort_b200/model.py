@@ -103,6 +103,11 @@ class DecodeModel:
             self.layers.append(None)
         self.layers[i] = (wq, wk, wv, wo, w1, w2, w3, attn_norm, ffn_norm)
 
+    def set_moe(self, i: int, gate: torch.Tensor):
+        """layers.i.feed_forward.gate [n_experts, dim] f16 (loader.swift:208-212); the layer's w1/w2/w3 hold n_experts experts."""
+        check(self._L.effort_model_set_moe(self._h, i, gate.data_ptr(), gate.shape[0]), "effort_model_set_moe")
+        self.layers[i] = self.layers[i] + (gate,)
+
     def set_head(self, norm: torch.Tensor, output_core: torch.Tensor, tok_embeddings: torch.Tensor):
         check(self._L.effort_model_set_head(self._h, norm.data_ptr(), output_core.data_ptr(),
                                             tok_embeddings.data_ptr()), "effort_model_set_head")
@@ -152,6 +157,36 @@ class DecodeModel:
         m.set_head(norm_vec(), out_core, _rand_w(cfg.vocab, cfg.dim, gen, scale=1.0))
         torch.cuda.synchronize()
         torch.cuda.empty_cache()
+        return m
+
+    @classmethod
+    def random_init_moe(cls, cfg: MistralConfig = MistralConfig(), n_experts: int = 4, seed: int = 1234,
+                        ctx: Optional[ops.Context] = None, norm_jitter: float = 0.1) -> "DecodeModel":
+        """A Mixtral-shaped random model (runNetwork.swift:185-200): attention as random_init, every layer's MLP with
+        `n_experts` experts (buckets / stats / probes concatenated along the expert dimension, loader.swift:113-166) and a
+        dense gate.  The reference layout tensors stay on the ExpertWeights objects for the CPU restatement."""
+        m = cls(cfg, ctx)
+        gen = torch.Generator(device="cuda").manual_seed(seed)
+        kvd = cfg.n_kv_heads * cfg.head_dim
+
+        def one(out_dim, in_dim):
+            return ops.bucketize(_rand_w(out_dim, in_dim, gen))
+
+        def make(out_dim, in_dim, e=1):
+            ts = [one(out_dim, in_dim) for _ in range(e)]
+            t = {k: torch.cat([x[k] for x in ts]) for k in ts[0]}
+            return ops.ExpertWeights(t["buckets"], t["bucket.stats"], t["probes"], inDim=in_dim, outDim=out_dim, numExperts=e)
+
+        def norm_vec():
+            return (1.0 + norm_jitter * torch.randn(cfg.dim, generator=gen, device="cuda")).half()
+
+        for i in range(cfg.n_layers):
+            m.set_layer(i, make(cfg.dim, cfg.dim), make(kvd, cfg.dim), make(kvd, cfg.dim), make(cfg.dim, cfg.dim),
+                        make(cfg.hidden_dim, cfg.dim, n_experts), make(cfg.dim, cfg.hidden_dim, n_experts),
+                        make(cfg.hidden_dim, cfg.dim, n_experts), norm_vec(), norm_vec())
+            m.set_moe(i, _rand_w(n_experts, cfg.dim, gen, scale=0.5))
+        m.set_head(norm_vec(), _rand_w(cfg.vocab, cfg.dim, gen), _rand_w(cfg.vocab, cfg.dim, gen, scale=1.0))
+        torch.cuda.synchronize()
         return m
 
     @classmethod

@@ -252,6 +252,11 @@ int effort_model_set_layer(effort_model_t* m, int layer, const effort_weights_t*
                            const effort_weights_t* wv, const effort_weights_t* wo, const effort_weights_t* w1,
                            const effort_weights_t* w2, const effort_weights_t* w3, const void* attn_norm_dev,
                            const void* ffn_norm_dev);
+/* Mixture of experts (runNetwork.swift:185-200, loader.swift:208-212): `gate_dev` = layers.N.feed_forward.gate [n_experts,
+ * dim] f16; the layer's w1 / w2 / w3 handles must hold n_experts experts.  Per token: gate logits = basicMul(rmsNorm(h) *
+ * ffn_norm, gate), the two largest (device indices, read by the expert GEMVs as expNo -- no host sync), softmax over
+ * the two, h += gateVal_i * w2_e(silu(w1_e x) * w3_e x) for both.  Fused chain only (effort_model_set_chain 2). */
+int effort_model_set_moe(effort_model_t* m, int layer, const void* gate_dev, int n_experts);
 /* model.norm [dim] f16, output.core [vocab,dim] f16, tok_embeddings.core [vocab,dim] f16 (loader.swift:254-272) */
 int effort_model_set_head(effort_model_t* m, const void* norm_dev, const void* output_core_dev,
                           const void* tok_embeddings_dev);

@@ -37,7 +37,13 @@ class RefModel:
         self.vc = [[] for _ in layers]
         self.pos = 0
 
-    def _mul(self, v, w, effort):
+    def _mul(self, v, w, effort, exp_no=0):
+        if w.get("n_experts", 1) > 1:   # expNo selects the expert's rows / probes (bucketMul.metal:49,143)
+            r = O.bucket_mul(v, w["buckets"], w["stats"], w["probes"], w["in"], w["out"], effort, exp_no=exp_no)
+            return r["out32"]
+        return self._mul1(v, w, effort)
+
+    def _mul1(self, v, w, effort):
         # expertMul routing (expertMul.swift:20-38): Q4 with buckets -> zero + bucketMulQ4 + outliers; Q4 without ->
         # dense basicMul on `core`; FP16 -> bucketMul
         kind = w.get("kind", "fp16")
@@ -71,6 +77,16 @@ class RefModel:
                 out[hh] = p @ V[:, hh // rep, :]                                   # sumScores32 aux.metal:379-393
             h = h + self._mul(out.reshape(-1), L["wo"], effort)
             fx = rmsnorm_mul(h, L["ffn_norm"])
+            if "gate" in L:   # runNetwork.swift:185-200
+                gl, _ = O.basic_mul(fx, L["gate"], cast_v=True)
+                order = sorted(range(len(gl)), key=lambda e: (-float(gl[e]), e))[:2]      # mpsTopK(2), ties: lower index
+                gv = np.exp(gl[order].astype(np.float32))
+                gv = gv / gv.sum()                                                         # gateVals.softmax()
+                for e, g in zip(order, gv):
+                    x1, x3 = self._mul(fx, L["w1"], effort, e), self._mul(fx, L["w3"], effort, e)
+                    x2 = (x3 * x1 / (1.0 + np.exp(-x1))).astype(np.float32)
+                    h = h + np.float32(g) * self._mul(x2, L["w2"], effort, e)
+                continue
             x1, x3 = self._mul(fx, L["w1"], effort), self._mul(fx, L["w3"], effort)
             x2 = (x3 * x1 / (1.0 + np.exp(-x1))).astype(np.float32)               # silu32b matrix.metal:25-34
             h = h + self._mul(x2, L["w2"], effort)

@@ -236,3 +236,32 @@ def test_q4_decode_matches_cpu_restatement():
             want = ref.step(t, 0.5)
             assert O.cossim(got, want) > 0.9995
             assert m.next_token() == int(np.argmax(got))
+
+
+def test_moe_decode_matches_cpu_restatement():
+    """Mixtral-style routing (runNetwork.swift:185-200): dense gate, top-2 on the device, the expert index reaches the
+    GEMVs as a device scalar (expNo), outputs weighted by the softmaxed gate values -- against the CPU restatement."""
+    import torch
+    from effort_b200.model import DecodeModel, MistralConfig
+    cfg = MistralConfig(n_layers=2, vocab=1024, max_seq=32)
+    m = DecodeModel.random_init_moe(cfg, n_experts=4, seed=9)
+    layers = []
+    for L in m.layers:
+        d = {}
+        for n, ew in zip(["wq", "wk", "wv", "wo", "w1", "w2", "w3"], L[:7]):
+            d[n] = {"buckets": _cpu(ew.buckets), "stats": _cpu(ew.stats), "probes": _cpu(ew.probes), "in": ew.inSize,
+                    "out": ew.outSize, "n_experts": ew.numExperts}
+        d["attn_norm"], d["ffn_norm"], d["gate"] = _cpu(L[7]), _cpu(L[8]), _cpu(L[9])
+        layers.append(d)
+    ref = RefModel(layers, _cpu(m.head[0]), _cpu(m.head[1]), _cpu(m.head[2]))
+    for use_graph in (False, True):
+        m.set_graphs(use_graph)
+        m.reset()
+        ref.pos, ref.kc, ref.vc = 0, [[] for _ in layers], [[] for _ in layers]
+        for t in (1, 17, 400):
+            m.step(torch.tensor([t], dtype=torch.int32, device="cuda"), effort=0.5)
+            torch.cuda.synchronize()
+            got = m.logits().cpu().numpy()
+            want = ref.step(t, 0.5)
+            assert O.cossim(got, want) > 0.9995
+            assert m.next_token() == int(np.argmax(got))
