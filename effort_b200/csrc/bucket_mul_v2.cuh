@@ -12,10 +12,12 @@
 //    (bucketMul.metal:236).  kCutBisect keeps the bit-exact replay of the reference's loop (cutoff.cuh, four warps).
 //  * selection list: 2 bytes per selected row ((local input << 4) | rank) written conflict-free with one ballot per
 //    rank; the row's HBM offset is rebuilt at issue time from a per-input base (works for both row layouts).
-//  * streaming: selected row slices are STAGED through a per-warp shared-memory ring by asynchronous copies
-//    (STAGE_LDGSTS: 16-byte cp.async per lane, completion by cp.async groups; STAGE_BULK: one cp.async.bulk = TMA
-//    unit copy per row slice, completion on an mbarrier): kUnitRows rows per unit, D units always in flight per
-//    warp at no register cost, independent of how fast the accumulate loop drains them.
+//  * streaming: selected row slices are STAGED through a per-warp shared-memory ring by 16-byte cp.async copies
+//    (completion by cp.async groups): units of up to kUnitRows consecutive ranks of one input, D units always in
+//    flight per warp at no register cost, independent of how fast the accumulate loop drains them.  (A variant with
+//    one cp.async.bulk per unit into the same per-warp rings measured 12-15 % slower and was dropped; the TMA
+//    pipeline with a dedicated producer warp lives in bucket_mul_v3.cuh, the warp-pair design in bucket_mul_v4.cuh.)
+//    This kernel is the generic path: any row layout (input-major, rank-major = NO_REPACK, slice-major) and Q4.
 //  * cross-CTA reduction: no partial tiles, no integrate launch.  A CTA sums its 16 warp tiles and adds the result
 //    into `out` with red.global.add.v4.f32 (one 16-byte reduction per thread).  Overwrite semantics (FP16 bucketMul
 //    overwrites out, bucketMul.metal:133) are provided in-kernel: every CTA zeroes its share of its column slice
@@ -42,7 +44,6 @@ constexpr int kV2MaxInputs = kV2Threads;  // inputs per selection pass (one per 
 enum VMode : int { kVPlain = 0, kVNorm = 1, kVSilu = 2 };
 enum OutMode : int { kOutOverwrite = 0, kOutAccumulate = 1 };
 enum CutMode : int { kCutSelect = 0, kCutBisect = 1 };
-enum StageMode : int { kStageLdgsts = 0, kStageBulk = 1 };
 
 struct V2Problem {
     const float* v;          // [in] input (kVPlain); residual stream h (kVNorm); x1 (kVSilu)
@@ -59,6 +60,8 @@ struct V2Problem {
     unsigned* sync;          // [CS][2] arrive / depart counters of the overwrite protocol (zero between launches)
     uint32_t* sel_counts;    // [RS] rows selected per row split (written by slice 0)
     float* cutoff_out;       // CTA 0 of the problem stores the cutoff
+    float* cutoff_hint;      // [E] per-matrix memory of the last cutoff (x the rmsNorm denominator in kVNorm): rows the
+                             // hint selects are prefetched into L2 while the real cutoff is computed (bucket_mul_v4)
     unsigned* err_flag;      // set when the overwrite barrier times out
     unsigned long long* trace;
     float norm_eps;
@@ -83,7 +86,6 @@ struct V2Header {
     int warp_cnt[kV2Warps];
     int warp_rows[kV2Warps];
     int next_unit;                // streaming: next unit of the list nobody has taken yet
-    unsigned long long mbar[kV2Warps][8];
 };
 
 // dynamic smem: [pad][tiles 16 x 8 KB][header][sbase 512 x u32][sval 512 x f32][sstat (Q4) 512 x 8 x f32][list cap x u16][ring]
@@ -231,7 +233,7 @@ __device__ __forceinline__ void accumulate_unit_fp16(uint32_t base_lane, float v
     for (int r = 0; r < N; r++) RmwFp16<VEC, 0>::store(a[r], acc[r]);
 }
 
-template <int SLOTS, int VEC, int CUT, int STAGE, int D>
+template <int SLOTS, int VEC, int CUT, int D>
 __global__ void __launch_bounds__(kV2Threads, 1)
 bucket_mul_v2_kernel(const __grid_constant__ V2Batch batch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -323,11 +325,6 @@ bucket_mul_v2_kernel(const __grid_constant__ V2Batch batch) {
         for (uint32_t a = ring_saddr + (uint32_t)lane * 16u; a < ring_saddr + (uint32_t)(D * kUnitBytes); a += 512u)
             asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory");  // lanes past a narrow slice read zeros
         if (tid < 16) hdr.sel_acc[tid >> 1][tid & 1] = 0u;
-        if constexpr (STAGE == kStageBulk) {
-            if (lane < 8) mbar_init((uint32_t)__cvta_generic_to_shared(&hdr.mbar[warp][lane]), 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        }
     }
     __syncthreads();  // select counters / barriers initialised before any warp uses them
     V2_TRACE(1);
@@ -456,7 +453,6 @@ bucket_mul_v2_kernel(const __grid_constant__ V2Batch batch) {
     constexpr uint32_t kHdrOff = kUnitRows * kRowStride;  // unit header: [0..3] multipliers, [4] unit code
 
     unsigned total_sel = 0;
-    uint32_t ring_phase = 0u;
     // ---- passes over the inputs of this row split (one pass for every Mistral shape) ----
     for (int j0 = 0; j0 < n_in; j0 += NT) {
         const int j = j0 + tid;
@@ -557,18 +553,9 @@ bucket_mul_v2_kernel(const __grid_constant__ V2Batch batch) {
                 const uint32_t jj = code >> 6, r0 = (code >> 2) & 15u;
                 const int n = (int)(code & 3u) + 1;
                 const uint32_t ubase = sbase[jj] + r0 * rstride16;
-                if constexpr (STAGE == kStageLdgsts) {
 #pragma unroll
-                    for (int k2 = 0; k2 < 2; k2++)
-                        if (prow[k2] < n) cp_async16(slot + pdst[k2], bk16 + (size_t)(ubase + psrc[k2]), pol);
-                } else {
-                    // the rows of a unit are contiguous in the slice-major device layout: ONE bulk copy per unit
-                    if (lane == 0) {
-                        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&hdr.mbar[warp][slot_i]);
-                        mbar_expect_tx(bar, n * seg_bytes);
-                        bulk_g2s(slot, bk16 + (size_t)ubase, n * seg_bytes, bar, pol);
-                    }
-                }
+                for (int k2 = 0; k2 < 2; k2++)
+                    if (prow[k2] < n) cp_async16(slot + pdst[k2], bk16 + (size_t)(ubase + psrc[k2]), pol);
                 if constexpr (SLOTS == 16) {
                     if (lane == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + kHdrOff), "f"(sval[jj]) : "memory");
                 } else {
@@ -579,27 +566,19 @@ bucket_mul_v2_kernel(const __grid_constant__ V2Batch batch) {
                 }
             }
             if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(slot + kHdrOff + 16u), "r"(code) : "memory");
-            if constexpr (STAGE == kStageLdgsts) cp_async_commit();
+            cp_async_commit();
         };
 #pragma unroll
         for (int m = 0; m < D; m++) issue_next(m);
         int head = 0;
-        uint32_t phase_bits = ring_phase;  // bulk: parity of every slot's barrier
 #pragma unroll 1
         for (;;) {
             const uint32_t slot = ring_saddr + (uint32_t)head * kUnitBytes;
-            if constexpr (STAGE == kStageLdgsts) cp_async_wait<D - 1>();
+            cp_async_wait<D - 1>();
             __syncwarp();
             uint32_t code;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(slot + kHdrOff + 16u));
             if (code == kEmpty) break;
-            if constexpr (STAGE == kStageBulk) {
-                if (!mbar_wait((uint32_t)__cvta_generic_to_shared(&hdr.mbar[warp][head]), (phase_bits >> head) & 1u)) {
-                    if (pb.err_flag && lane == 0) atomicExch(pb.err_flag, 2u);
-                    break;
-                }
-                phase_bits ^= 1u << head;
-            }
             const int n = (int)(code & 3u) + 1;
             if constexpr (SLOTS == 16) {
                 float val;
@@ -641,8 +620,7 @@ bucket_mul_v2_kernel(const __grid_constant__ V2Batch batch) {
             issue_next(head);
             head = (head + 1) & (D - 1);
         }
-        if constexpr (STAGE == kStageLdgsts) cp_async_wait<0>();
-        ring_phase = phase_bits;
+        cp_async_wait<0>();
     }
     if (pb.sel_counts && slice == 0 && tid == 0) pb.sel_counts[rsp] = total_sel;
     __syncthreads();

@@ -51,6 +51,14 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// x / d with a shared correctly rounded reciprocal r = rn(1/d): one Newton step on the quotient (q = x*r; q += (x - q*d)*r),
+// the correctly rounded quotient for every finite, normal operand pair -- 3 instructions instead of the division's subroutine
+// call (the 32 normalisations of a select thread sit on the kernel's critical path)
+__device__ __forceinline__ float div_by(float x, float d, float r) {
+    const float q = x * r;
+    return fmaf(fmaf(-q, d, x), r, q);
+}
+
 // count of keys above the threshold, 32 keys (16 bf16x2 registers) per thread
 __device__ __forceinline__ uint32_t count_gt32(const uint32_t (&keys)[16], uint32_t th) {
     const __nv_bfloat162 t = as_bf162(splat_bf16(th));
@@ -188,7 +196,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
             mbar_init((uint32_t)__cvta_generic_to_shared(&hdr.empty_bar[0][0] + s), 1);
         }
         if (lane == 0) { hdr.ticket = 0u; hdr.sel_rows = 0; }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // (the __syncthreads before the first use orders the initialisation: no cluster, no async-proxy user here)
     }
     V2_TRACE(1);
     pdl_wait();
@@ -201,6 +209,36 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
         my_v = pb.v[i];
         if (vmode == kVSilu) my_x3 = pb.v2[i];
         if (vmode == kVNorm) my_nw = __half2float(pb.norm_w[i]);
+    }
+    const int seg_bytes0 = slice_cols * 2;
+    const uint4* bk16p = reinterpret_cast<const uint4*>(pb.bk + (size_t)pb.in * P * ((size_t)slice * pb.W));
+    if (pb.cutoff_hint && (CUT != kCutSelect || !sel_warp)) {
+        // Speculative L2 prefetch.  The cutoff moves little from token to token, so while the select warps compute the real
+        // one the other warps test their rows against the LAST cutoff this matrix saw (kVNorm: scaled by that call's
+        // rmsNorm denominator, which is not known yet either) and ask the L2 for the prefix of ranks it selects: one
+        // cp.async.bulk.prefetch per input.  Purely a hint: the real masks below decide what is streamed.
+        const float hint = pb.cutoff_hint[e_no];
+        auto spec = [&](int jj, const float (&st)[16], float vraw) {
+            int n = 0;
+#pragma unroll
+            for (int rho = 0; rho < 16; rho++) n += (rho == n && rho < P && row_selected(hint, st[rho], vraw)) ? 1 : 0;
+            if (n > 0) {
+                const int i = rsp + jj * RS;
+                const uint4* src = bk16p + (((size_t)e_no * pb.in * P * C + (size_t)i * P * slice_cols) >> 3);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(n * seg_bytes0) : "memory");
+            }
+        };
+        auto raw = [&](float x, float x3, float nw) { return vmode == kVSilu ? silu_mul(x, x3) : (vmode == kVNorm ? x * nw : x); };
+        if (tid < n_in) spec(tid, sel_stat, raw(my_v, my_x3, my_nw));
+        if (CUT == kCutSelect && tid >= kV4SelWarps * 32 && tid < 2 * kV4SelWarps * 32 && tid - kV4SelWarps * 32 < n_in) {
+            const int j2 = tid - kV4SelWarps * 32;  // the select warps' inputs: covered by the next four warps
+            float st2[16];
+#pragma unroll
+            for (int rho = 0; rho < 16; rho++) st2[rho] = 0.f;
+            load_stats(j2, st2);
+            const int i2 = rsp + j2 * RS;
+            spec(j2, st2, raw(pb.v[i2], vmode == kVSilu ? pb.v2[i2] : 0.f, vmode == kVNorm ? __half2float(pb.norm_w[i2]) : 1.f));
+        }
     }
     if constexpr (CUT == kCutSelect) {
         if (sel_warp) {
@@ -232,14 +270,15 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                 for (int w = 0; w < kV4SelWarps; w++) t += hdr.red[w];
                 denom = sqrtf(t / (float)pb.in + pb.norm_eps);
                 if (tid == 0) hdr.denom = denom;
+                const float rden = __frcp_rn(denom);
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     const uint32_t nw[4] = {nwv[c].x, nwv[c].y, nwv[c].z, nwv[c].w};
 #pragma unroll
                     for (int m = 0; m < 4; m++) {
                         const float2 wf = __half22float2(*reinterpret_cast<const __half2*>(&nw[m]));
-                        vv[8 * c + 2 * m] = (vv[8 * c + 2 * m] / denom) * wf.x;
-                        vv[8 * c + 2 * m + 1] = (vv[8 * c + 2 * m + 1] / denom) * wf.y;
+                        vv[8 * c + 2 * m] = div_by(vv[8 * c + 2 * m], denom, rden) * wf.x;
+                        vv[8 * c + 2 * m + 1] = div_by(vv[8 * c + 2 * m + 1], denom, rden) * wf.y;
                     }
                 }
             }
@@ -310,11 +349,12 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
     const float cutoff = hdr.cutoff;
     if (vmode == kVNorm) {
         denom = hdr.denom;
-        my_v = (my_v / denom) * my_nw;
+        my_v = div_by(my_v, denom, __frcp_rn(denom)) * my_nw;
     } else if (vmode == kVSilu) {
         my_v = silu_mul(my_v, my_x3);
     }
     if (pb.cutoff_out && lb == 0 && tid == 0) *pb.cutoff_out = cutoff;
+    if (pb.cutoff_hint && lb == 0 && tid == 0) pb.cutoff_hint[e_no] = cutoff * (vmode == kVNorm ? denom : 1.f);
     V2_TRACE(6);
 
     const int seg_bytes = slice_cols * 2;

@@ -57,6 +57,7 @@ struct effort_weights {
     __half* probes_own = nullptr;  // copy of the caller's probes (8 KB per expert)
     __half* st16 = nullptr;      // FP16: one stat per row (row order == fast-path bucket order)
     float* st32 = nullptr;       // Q4
+    float* hint = nullptr;       // [n_experts] last cutoff seen (bucket_mul_v4's L2 prefetch hint); +inf = none yet
     size_t owned = 0;
     int layout = kInputMajor;
     int device = 0;
@@ -89,6 +90,7 @@ struct effort_ctx {
                                           // 2 = one TMA producer warp + byte ring (slice-major FP16 weights; measured slower)
                                           // 0 = per-warp cp.async rings, units of <= 4 rows (any layout, Q4)
     int engine = 2;                       // 2 = bucket_mul_v2_kernel, 1 = round-1 fused kernel + integrate
+    int prefetch = 1;                     // bucket_mul_v4: speculative L2 prefetch from the previous cutoff of the matrix
     int dynamic = 0;                      // v2 per-warp rings: units from a shared counter (1) or static round robin (0, measured faster)
     int last_rs[8] = {0};                 // row splits of the last v2 launch per batch slot (effort_last_selected)
     bool last_was_v2 = false;
@@ -153,6 +155,7 @@ extern "C" int effort_ctx_create(int device, effort_ctx_t** ctx_out) {
     { const char* e = getenv("EFFORT_STAGE"); if (e) c->stage_mode = !strcmp(e, "ldgsts") ? 0 : !strcmp(e, "tma") ? 2 : 3; }
     { const char* e = getenv("EFFORT_ENGINE"); if (e && atoi(e) == 1) c->engine = 1; }
     { const char* e = getenv("EFFORT_DYN"); if (e) c->dynamic = atoi(e) ? 1 : 0; }
+    { const char* e = getenv("EFFORT_PREFETCH"); if (e) c->prefetch = atoi(e) ? 1 : 0; }
     if (getenv("EFFORT_TRACE")) {
         CK(cudaMalloc(&c->trace, sizeof(unsigned long long) * 16 * c->n_sms));
         CK(cudaMemset(c->trace, 0, sizeof(unsigned long long) * 16 * c->n_sms));
@@ -171,6 +174,7 @@ extern "C" int effort_ctx_set_option(effort_ctx_t* c, const char* name, int valu
     if (!c || !name) return EFFORT_EINVAL;
     if (!strcmp(name, "engine")) { if (value != 1 && value != 2) return EFFORT_EINVAL; c->engine = value; return EFFORT_OK; }
     if (!strcmp(name, "stage")) { if (value != 0 && value != 2 && value != 3) return EFFORT_EINVAL; c->stage_mode = value; return EFFORT_OK; }
+    if (!strcmp(name, "prefetch")) { if (value != 0 && value != 1) return EFFORT_EINVAL; c->prefetch = value; return EFFORT_OK; }
     if (!strcmp(name, "dynamic")) { if (value != 0 && value != 1) return EFFORT_EINVAL; c->dynamic = value; return EFFORT_OK; }
     return EFFORT_EINVAL;
 }
@@ -273,6 +277,12 @@ extern "C" int effort_weights_create(const void* buckets_dev, const void* stats_
                            cudaMemcpyDeviceToDevice, stream));
         w->probes = w->probes_own;
         w->owned += (size_t)n_experts * EFFORT_PROBES_COUNT * sizeof(__half);
+        {
+            std::vector<float> inf((size_t)n_experts, __builtin_inff());
+            CK(cudaMalloc(&w->hint, sizeof(float) * n_experts));
+            CK(cudaMemcpyAsync(w->hint, inf.data(), sizeof(float) * n_experts, cudaMemcpyHostToDevice, stream));
+            CK(cudaStreamSynchronize(stream));  // `inf` leaves scope
+        }
         if (kind == EFFORT_KIND_FP16) {
             const bool repack = !(flags & EFFORT_WEIGHTS_NO_REPACK);
             const bool slice_major = repack && !(flags & EFFORT_WEIGHTS_INPUT_MAJOR) &&
@@ -312,7 +322,7 @@ extern "C" int effort_weights_create(const void* buckets_dev, const void* stats_
 
 extern "C" int effort_weights_destroy(effort_weights_t* w) {
     if (!w) return EFFORT_OK;
-    cudaFree(w->bk_own); cudaFree(w->st16); cudaFree(w->st32); cudaFree(w->probes_own);
+    cudaFree(w->bk_own); cudaFree(w->st16); cudaFree(w->st32); cudaFree(w->probes_own); cudaFree(w->hint);
     delete w;
     return EFFORT_OK;
 }
@@ -506,6 +516,7 @@ static int launch_v2_batch(effort_ctx* ctx, const V2Call* calls, int n, int slot
         pb.sync = ctx->v2_sync + (size_t)(slot0 + k) * kV2MaxSlices * 2;
         pb.sel_counts = ctx->sel_counts + (size_t)(slot0 + k) * ctx->n_sms;
         pb.cutoff_out = ctx->cutoff + slot0 + k;
+        pb.cutoff_hint = ctx->prefetch ? w->hint : nullptr;
         pb.err_flag = ctx->v2_err;
         pb.trace = ctx->trace;
         pb.in = w->in; pb.C = w->C; pb.P = w->P; pb.q = effort_q(c.effort, w->n_probes); pb.layout = w->layout;
@@ -522,7 +533,6 @@ static int launch_v2_batch(effort_ctx* ctx, const V2Call* calls, int n, int slot
     batch.cta_begin[n] = cta;
     batch.list_cap = (list_cap + 63) & ~63;
     using L = V2Smem<SLOTS, VEC>;
-    const bool bulk = false;  // the per-warp cp.async.bulk rings of the first round-2 draft lost to cp.async and are not offered
     batch.dynamic = ctx->dynamic;
     const size_t smem = L::bytes(batch.list_cap, D);
     if (smem > kMaxSmem) return EFFORT_ESHAPE;
@@ -552,11 +562,9 @@ static int launch_v2_batch(effort_ctx* ctx, const V2Call* calls, int n, int slot
         const size_t smem3 = V3Smem::kFixed + (size_t)batch.ring_bytes;
         rc = bisect ? go(bucket_mul_v3_kernel<kCutBisect>, kV3Threads, smem3) : go(bucket_mul_v3_kernel<kCutSelect>, kV3Threads, smem3);
     } else if (bisect) {
-        rc = bulk ? go(bucket_mul_v2_kernel<SLOTS, VEC, kCutBisect, kStageBulk, D>, kV2Threads, smem)
-                  : go(bucket_mul_v2_kernel<SLOTS, VEC, kCutBisect, kStageLdgsts, D>, kV2Threads, smem);
+        rc = go(bucket_mul_v2_kernel<SLOTS, VEC, kCutBisect, D>, kV2Threads, smem);
     } else {
-        rc = bulk ? go(bucket_mul_v2_kernel<SLOTS, VEC, kCutSelect, kStageBulk, D>, kV2Threads, smem)
-                  : go(bucket_mul_v2_kernel<SLOTS, VEC, kCutSelect, kStageLdgsts, D>, kV2Threads, smem);
+        rc = go(bucket_mul_v2_kernel<SLOTS, VEC, kCutSelect, D>, kV2Threads, smem);
     }
     if (rc) return rc;
     LAUNCHED();

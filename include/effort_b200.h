@@ -92,8 +92,10 @@ int effort_ctx_set_cutoff_mode(effort_ctx_t* ctx, int mode);
  *              (slice-major FP16 weights; measured slower: the single producer's serial issue is the limit);
  *              0 sixteen self-serving warps with private cp.async rings, units of at most 4 rows
  *   "dynamic"  per-warp rings (stage 0/1) only: 0 (default) static round robin of the units, 1 units from a shared counter
+ *   "prefetch" 1 (default) stage 3 only: while the cutoff is being computed, rows that the matrix's PREVIOUS cutoff would
+ *              select are prefetched into L2 (a hint: the result does not depend on it); 0 off
  * Returns EFFORT_EINVAL for an unknown name or value.  Environment defaults: EFFORT_ENGINE, EFFORT_STAGE=bulk,
- * EFFORT_DYN. */
+ * EFFORT_DYN, EFFORT_PREFETCH. */
 int effort_ctx_set_option(effort_ctx_t* ctx, const char* name, int value);
 /* Non-zero once a fused kernel of this context gave up waiting for a co-resident CTA (2 s): its output is invalid.
  * Synchronises `stream`. */
