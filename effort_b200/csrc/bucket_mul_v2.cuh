@@ -60,8 +60,9 @@ struct V2Problem {
     unsigned* sync;          // [CS][2] arrive / depart counters of the overwrite protocol (zero between launches)
     uint32_t* sel_counts;    // [RS] rows selected per row split (written by slice 0)
     float* cutoff_out;       // CTA 0 of the problem stores the cutoff
-    float* cutoff_hint;      // [E] per-matrix memory of the last cutoff (x the rmsNorm denominator in kVNorm): rows the
-                             // hint selects are prefetched into L2 while the real cutoff is computed (bucket_mul_v4)
+    float* cutoff_hint;      // [E] per-matrix memory of the last cutoff (x the rmsNorm denominator in kVNorm): where
+                             // bucket_mul_v4's select starts looking (and what its optional L2 prefetch tests against)
+    int* rounds_out;         // optional: CTA 0 stores the number of select rounds it needed
     unsigned* err_flag;      // set when the overwrite barrier times out
     unsigned long long* trace;
     float norm_eps;
@@ -75,6 +76,7 @@ struct V2Batch {
     int list_cap;            // units
     int dynamic;             // 1: warps take units from a shared counter; 0: static round robin
     int ring_bytes;          // bucket_mul_v3_kernel: bytes of the producer's staging ring
+    int prefetch;            // bucket_mul_v4_kernel: speculative L2 prefetch of the rows the hint selects
     int cta_begin[kMulBatchMax + 1];
     V2Problem p[kMulBatchMax];
 };

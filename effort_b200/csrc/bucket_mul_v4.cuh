@@ -23,10 +23,16 @@
 namespace effort {
 
 constexpr int kV4Pairs = 8;                    // consumer / producer warp pairs
-constexpr int kV4Slots = 4;                    // ring slots per pair
-constexpr int kV4SlotData = 16 * 256;          // up to 16 rows of a full-width slice
-constexpr int kV4SlotBytes = kV4SlotData + 128;  // + header {val, n rows, row stride}, slots stay 128-byte aligned
+constexpr int kV4Units = 16;                   // units in flight per pair (descriptor slots; a power of two)
+constexpr int kV4RingBytes = 16 * 1024;        // staging bytes per pair: a first-in-first-out byte ring
 constexpr int kV4SelWarps = 4;
+
+struct __align__(16) V4Desc {
+    uint32_t off;      // byte offset of the unit's first row in the pair's ring
+    uint32_t n;        // rows (0 = stop marker)
+    float val;         // the input's multiplier
+    uint32_t rstride;  // bytes between the unit's rows in the ring
+};
 
 struct V4Header {
     CutoffSmem cut;                      // bisect mode scratch
@@ -35,8 +41,10 @@ struct V4Header {
     float cutoff, denom;
     int sel_rows;
     unsigned ticket;                     // next input a producer may take
-    unsigned long long full_bar[kV4Pairs][kV4Slots];
-    unsigned long long empty_bar[kV4Pairs][kV4Slots];
+    unsigned long long full_bar[kV4Pairs][kV4Units];
+    unsigned long long empty_bar[kV4Pairs][kV4Units];
+    V4Desc desc[kV4Pairs][kV4Units];
+    uint16_t usize[kV4Pairs][kV4Units];  // ring bytes / 16 a unit holds (incl. a wrap skip charged to it)
 };
 
 struct V4Smem {
@@ -44,11 +52,22 @@ struct V4Smem {
     static constexpr int kTileBytes = kTileFloats * 4;
     static constexpr size_t kHdrBytes = (sizeof(V4Header) + 127) & ~size_t(127);
     static constexpr size_t kBytes = (size_t)kTileBytes /*alignment slack*/ + (size_t)kV4Pairs * kTileBytes + kHdrBytes +
-                                     (size_t)kV2MaxInputs * (4 + 4 + 4) + 128 + (size_t)kV4Pairs * kV4Slots * kV4SlotBytes;
+                                     (size_t)kV2MaxInputs * (4 + 4 + 4) + 128 + (size_t)kV4Pairs * kV4RingBytes;
 };
 
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// bounded mbarrier wait that lets the hardware park the warp (suspend-time hint) instead of spinning through the issue
+// slots the accumulating warps need; returns false after ~1 s (a bug, never a data condition)
+__device__ __forceinline__ bool mbar_wait_parked(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (int tries = 0; tries < (1 << 19) && !done; tries++) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(2000u) : "memory");
+    }
+    return done != 0;
 }
 
 // x / d with a shared correctly rounded reciprocal r = rn(1/d): one Newton step on the quotient (q = x*r; q += (x - q*d)*r),
@@ -71,19 +90,31 @@ __device__ __forceinline__ uint32_t count_gt32(const uint32_t (&keys)[16], uint3
     return (uint32_t)bf162_count(__hadd2(c0, c1));  // 0..32
 }
 
-// exact select on the first kV4SelWarps warps (gt = thread index inside the group): see select_cutoff (bucket_mul_v2.cuh)
-__device__ __forceinline__ float select_cutoff_group(const uint32_t (&keys)[16], int k, V4Header& hdr, int gt) {
+// Exact select on the first kV4SelWarps warps (gt = thread index inside the group).  Q(x) = [#{keys > x} >= k+1] is true
+// up to u = the key just below the (k+1)-th largest and false above; the cutoff key is u + 1 (0 when Q(0) is false).
+// A quaternary search over the 15-bit key space keeps an interval (L, R) with Q(L) true (L = -1: nothing known) and
+// Q(R) false and evaluates three interior thresholds per round (one pass over the keys, one 128-thread barrier).  Eight
+// rounds from scratch.  With a hint -- the key of the cutoff this matrix saw on the previous call -- the first round
+// brackets it (hint +- 16 keys = +- 12 % in value) and two more rounds finish when the guess holds; a miss only costs the
+// bracketing round.  The result does not depend on the hint.
+__device__ __forceinline__ float select_cutoff_group(const uint32_t (&keys)[16], int k, V4Header& hdr, int gt, uint32_t hint_key,
+                                                     int* rounds_out) {
     const int lane = gt & 31, gw = gt >> 5;
-    uint32_t u = 0;
-    bool any = true;
     const unsigned need = (unsigned)(k + 1);
+    int L = -1, R = 0x7FFF;
+    bool first = hint_key > 16u && hint_key < 0x7F00u;
+    int round = 0;
 #pragma unroll 1
-    for (int round = 0; round < 8; round++) {
-        const int b = 14 - 2 * round;
-        uint32_t th1, th2, th3;
-        if (round == 0) { th1 = 0u; th2 = 1u << 14; th3 = 0x7FFFu; }
-        else { th1 = u | (1u << b); th2 = u | (2u << b); th3 = u | (3u << b); }
-        const uint32_t c1 = count_gt32(keys, th1), c2 = count_gt32(keys, th2), c3 = count_gt32(keys, th3);
+    while (R - L > 1) {
+        int p1, p2, p3;
+        if (first) { p1 = (int)hint_key - 16; p2 = (int)hint_key; p3 = (int)hint_key + 16; }
+        else {
+            const int w = R - L;
+            p1 = L + max(1, w >> 2); p2 = L + max(1, w >> 1); p3 = L + max(1, (3 * w) >> 2);
+            p2 = min(p2, R - 1); p3 = min(p3, R - 1);
+        }
+        first = false;
+        const uint32_t c1 = count_gt32(keys, (uint32_t)p1), c2 = count_gt32(keys, (uint32_t)p2), c3 = count_gt32(keys, (uint32_t)p3);
         const uint32_t a = __reduce_add_sync(0xffffffffu, c1 | (c2 << 16));
         const uint32_t bsum = __reduce_add_sync(0xffffffffu, c3);
         if (lane == 0) hdr.sel_slot[round & 1][gw] = make_uint2(a, bsum);
@@ -95,17 +126,15 @@ __device__ __forceinline__ float select_cutoff_group(const uint32_t (&keys)[16],
             A += s.x;
             B += s.y;
         }
-        const unsigned g1 = A & 0xFFFFu, g2 = A >> 16, g3 = B;
-        if (round == 0) {
-            any = g1 >= need;
-            if (g2 >= need) u = 1u << 14;
-        } else {
-            const unsigned j = (g1 >= need ? 1u : 0u) + (g2 >= need ? 1u : 0u) + (g3 >= need ? 1u : 0u);
-            u |= j << b;
-        }
+        const bool q1 = (A & 0xFFFFu) >= need, q2 = (A >> 16) >= need, q3 = B >= need;
+        if (!q1) R = p1;
+        else if (!q2) { L = p1; R = p2; }
+        else if (!q3) { L = p2; R = p3; }
+        else L = p3;
+        round++;
     }
-    const uint32_t t = any ? (u + 1u) : 0u;
-    return __uint_as_float(t << 16);
+    if (rounds_out && gt == 0) *rounds_out = round;
+    return __uint_as_float((uint32_t)(L + 1) << 16);
 }
 
 template <int CUT>
@@ -146,7 +175,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
     p += (size_t)kV2MaxInputs * 4;
     p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 127) & ~uintptr_t(127));
     float* ring_f = reinterpret_cast<float*>(p);
-    const uint32_t ring_saddr = (uint32_t)__cvta_generic_to_shared(p) + (uint32_t)pair * (uint32_t)(kV4Slots * kV4SlotBytes);
+    const uint32_t ring_saddr = (uint32_t)__cvta_generic_to_shared(p) + (uint32_t)pair * (uint32_t)kV4RingBytes;
 
     pdl_trigger();
     if (pb.exp_no) pdl_wait();
@@ -191,7 +220,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
         }
     }
     if (warp == NC) {  // first producer warp: the ring barriers
-        for (int s = lane; s < NC * kV4Slots; s += 32) {
+        for (int s = lane; s < NC * kV4Units; s += 32) {
             mbar_init((uint32_t)__cvta_generic_to_shared(&hdr.full_bar[0][0] + s), 33);  // 32 cp.async arrivals + the header's
             mbar_init((uint32_t)__cvta_generic_to_shared(&hdr.empty_bar[0][0] + s), 1);
         }
@@ -212,7 +241,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
     }
     const int seg_bytes0 = slice_cols * 2;
     const uint4* bk16p = reinterpret_cast<const uint4*>(pb.bk + (size_t)pb.in * P * ((size_t)slice * pb.W));
-    if (pb.cutoff_hint && (CUT != kCutSelect || !sel_warp)) {
+    if (batch.prefetch && pb.cutoff_hint && (CUT != kCutSelect || !sel_warp)) {
         // Speculative L2 prefetch.  The cutoff moves little from token to token, so while the select warps compute the real
         // one the other warps test their rows against the LAST cutoff this matrix saw (kVNorm: scaled by that call's
         // rmsNorm denominator, which is not known yet either) and ask the L2 for the prefix of ranks it selects: one
@@ -291,7 +320,13 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                 keys[4 * c] = k4[0]; keys[4 * c + 1] = k4[1]; keys[4 * c + 2] = k4[2]; keys[4 * c + 3] = k4[3];
             }
             V2_TRACE(3);
-            const float cut = select_cutoff_group(keys, EFFORT_PROBES_MAX - pb.q, hdr, tid);
+            uint32_t hint_key = 0u;
+            if (pb.cutoff_hint) {  // last cutoff of this matrix (kVNorm: stored times that call's denominator)
+                const float hc = pb.cutoff_hint[e_no] / denom;
+                hint_key = (hc > 0.f && hc < 3e38f) ? (__float_as_uint(hc) >> 16) : 0u;
+            }
+            const float cut = select_cutoff_group(keys, EFFORT_PROBES_MAX - pb.q, hdr, tid, hint_key,
+                                                  (lb == 0) ? pb.rounds_out : nullptr);
             if (tid == 0) hdr.cutoff = cut;
         }
     }
@@ -367,8 +402,9 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
     const uint4* bk16 = reinterpret_cast<const uint4*>(pb.bk + (size_t)pb.in * P * ((size_t)slice * pb.W));  // slice-major
     const uint32_t rs16 = (uint32_t)(seg_bytes >> 4);
 
-    int slot = 0, filled = 0;
-    uint32_t phase = 0u;  // consumer: full-barrier parities; producer: empty-barrier parities (bit per slot)
+    // pair state.  Both sides count units (seq); unit s uses descriptor slot s % kV4Units, barrier phase (s / kV4Units) & 1.
+    // Producer only: ring head, free bytes, oldest unit not yet reclaimed.
+    uint32_t seq = 0, tail_seq = 0, head = 0, free_b = kV4RingBytes;
     // ---- passes over the inputs of this row split (one pass for every Mistral shape) ----
     for (int j0 = 0; j0 < n_in; j0 += NT) {
         const int j = j0 + tid;
@@ -406,26 +442,37 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
         if (!consumer) {
             // ---- 3a. producer of pair `pair`: the next input nobody has taken, its selected runs into the ring ----
             const uint32_t ticket_saddr = (uint32_t)__cvta_generic_to_shared(&hdr.ticket);
-            auto fill = [&](uint32_t src16, int len, float val) {  // len rows (0 = stop marker) into the next slot
-                const uint32_t sa = ring_saddr + (uint32_t)slot * kV4SlotBytes;
-                if (filled >= kV4Slots) {  // the slot's previous unit must have been consumed
-                    if (!mbar_wait((uint32_t)__cvta_generic_to_shared(&hdr.empty_bar[pair][slot]), (phase >> slot) & 1u)) {
-                        if (pb.err_flag && lane == 0) atomicExch(pb.err_flag, 3u);
-                    }
-                    phase ^= 1u << slot;
+            auto reclaim = [&]() {  // wait for the consumer to release the oldest unit, take its bytes back
+                const uint32_t ts = tail_seq & (kV4Units - 1);
+                if (!mbar_wait_parked((uint32_t)__cvta_generic_to_shared(&hdr.empty_bar[pair][ts]), (tail_seq / kV4Units) & 1u)) {
+                    if (pb.err_flag && lane == 0) atomicExch(pb.err_flag, 3u);
                 }
-                filled++;
+                free_b += (uint32_t)hdr.usize[pair][ts] * 16u;
+                tail_seq++;
+            };
+            auto fill = [&](uint32_t src16, int len, float val) {  // len rows (0 = stop marker) as the next unit
+                const uint32_t bytes = (uint32_t)(len * seg_bytes);
+                const uint32_t skip = (head + bytes > (uint32_t)kV4RingBytes) ? ((uint32_t)kV4RingBytes - head) : 0u;
+                while (free_b < bytes + skip || seq - tail_seq >= (uint32_t)kV4Units) reclaim();
+                const uint32_t off = skip ? 0u : head;
+                const uint32_t slot = seq & (kV4Units - 1);
+                const uint32_t sa = ring_saddr + off;
                 const int pieces = len * (int)rs16;
                 const uint4* src = bk16 + src16;
                 for (int q = lane; q < pieces; q += 32) cp_async16(sa + (uint32_t)q * 16u, src + q, pol);
-                if (lane == 0)
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sa + (uint32_t)kV4SlotData), "r"(__float_as_uint(val)),
-                                 "r"((uint32_t)len), "r"((uint32_t)seg_bytes), "r"(0u) : "memory");
+                if (lane == 0) {
+                    hdr.usize[pair][slot] = (uint16_t)((bytes + skip) >> 4);
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"((uint32_t)__cvta_generic_to_shared(&hdr.desc[pair][slot])),
+                                 "r"(off), "r"((uint32_t)len), "r"(__float_as_uint(val)), "r"((uint32_t)seg_bytes) : "memory");
+                }
                 const uint32_t fb = (uint32_t)__cvta_generic_to_shared(&hdr.full_bar[pair][slot]);
                 cp_async_arrive_noinc(fb);  // arrives when this lane's copies have landed
                 __syncwarp();
-                if (lane == 0) mbar_arrive(fb);  // releases the header
-                slot = (slot + 1) & (kV4Slots - 1);
+                if (lane == 0) mbar_arrive(fb);  // releases the descriptor
+                seq++;
+                head = off + bytes;
+                free_b -= bytes + skip;
+                if (head >= (uint32_t)kV4RingBytes) head = 0u;
             };
 #pragma unroll 1
             for (;;) {
@@ -449,22 +496,23 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
             // ---- 3b. consumer ----
 #pragma unroll 1
             for (;;) {
-                const uint32_t sa = ring_saddr + (uint32_t)slot * kV4SlotBytes;
-                if (!mbar_wait((uint32_t)__cvta_generic_to_shared(&hdr.full_bar[pair][slot]), (phase >> slot) & 1u)) {
+                const uint32_t slot = seq & (kV4Units - 1);
+                if (!mbar_wait_parked((uint32_t)__cvta_generic_to_shared(&hdr.full_bar[pair][slot]), (seq / kV4Units) & 1u)) {
                     if (pb.err_flag && lane == 0) atomicExch(pb.err_flag, 2u);
                     break;
                 }
-                phase ^= 1u << slot;
-                uint32_t hv, hn, hs, hz;
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hv), "=r"(hn), "=r"(hs), "=r"(hz) : "r"(sa + (uint32_t)kV4SlotData));
+                seq++;
+                uint32_t hoff, hn, hv, hs;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hoff), "=r"(hn), "=r"(hv), "=r"(hs)
+                             : "r"((uint32_t)__cvta_generic_to_shared(&hdr.desc[pair][slot])));
                 const int n = (int)hn;
                 const uint32_t eb = (uint32_t)__cvta_generic_to_shared(&hdr.empty_bar[pair][slot]);
-                slot = (slot + 1) & (kV4Slots - 1);
                 if (n == 0) {
                     if (lane == 0) mbar_arrive(eb);
                     break;
                 }
                 const float val = __uint_as_float(hv);
+                const uint32_t sa = ring_saddr + hoff;
                 if (full_width) {
                     uint32_t a0 = sa + (uint32_t)(lane * LB);
                     int r = 0;

@@ -90,7 +90,9 @@ struct effort_ctx {
                                           // 2 = one TMA producer warp + byte ring (slice-major FP16 weights; measured slower)
                                           // 0 = per-warp cp.async rings, units of <= 4 rows (any layout, Q4)
     int engine = 2;                       // 2 = bucket_mul_v2_kernel, 1 = round-1 fused kernel + integrate
-    int prefetch = 1;                     // bucket_mul_v4: speculative L2 prefetch from the previous cutoff of the matrix
+    int prefetch = 0;                     // bucket_mul_v4: speculative L2 prefetch of the rows the previous cutoff selects
+                                          // (measured: no gain at effort 0.25, -13 % at 1.0: the gather is not DRAM-latency bound)
+    int use_hint = 1;                     // bucket_mul_v4: the select starts from the matrix's previous cutoff
     int dynamic = 0;                      // v2 per-warp rings: units from a shared counter (1) or static round robin (0, measured faster)
     int last_rs[8] = {0};                 // row splits of the last v2 launch per batch slot (effort_last_selected)
     bool last_was_v2 = false;
@@ -156,6 +158,7 @@ extern "C" int effort_ctx_create(int device, effort_ctx_t** ctx_out) {
     { const char* e = getenv("EFFORT_ENGINE"); if (e && atoi(e) == 1) c->engine = 1; }
     { const char* e = getenv("EFFORT_DYN"); if (e) c->dynamic = atoi(e) ? 1 : 0; }
     { const char* e = getenv("EFFORT_PREFETCH"); if (e) c->prefetch = atoi(e) ? 1 : 0; }
+    { const char* e = getenv("EFFORT_HINT"); if (e) c->use_hint = atoi(e) ? 1 : 0; }
     if (getenv("EFFORT_TRACE")) {
         CK(cudaMalloc(&c->trace, sizeof(unsigned long long) * 16 * c->n_sms));
         CK(cudaMemset(c->trace, 0, sizeof(unsigned long long) * 16 * c->n_sms));
@@ -174,6 +177,7 @@ extern "C" int effort_ctx_set_option(effort_ctx_t* c, const char* name, int valu
     if (!c || !name) return EFFORT_EINVAL;
     if (!strcmp(name, "engine")) { if (value != 1 && value != 2) return EFFORT_EINVAL; c->engine = value; return EFFORT_OK; }
     if (!strcmp(name, "stage")) { if (value != 0 && value != 2 && value != 3) return EFFORT_EINVAL; c->stage_mode = value; return EFFORT_OK; }
+    if (!strcmp(name, "hint")) { if (value != 0 && value != 1) return EFFORT_EINVAL; c->use_hint = value; return EFFORT_OK; }
     if (!strcmp(name, "prefetch")) { if (value != 0 && value != 1) return EFFORT_EINVAL; c->prefetch = value; return EFFORT_OK; }
     if (!strcmp(name, "dynamic")) { if (value != 0 && value != 1) return EFFORT_EINVAL; c->dynamic = value; return EFFORT_OK; }
     return EFFORT_EINVAL;
@@ -516,7 +520,8 @@ static int launch_v2_batch(effort_ctx* ctx, const V2Call* calls, int n, int slot
         pb.sync = ctx->v2_sync + (size_t)(slot0 + k) * kV2MaxSlices * 2;
         pb.sel_counts = ctx->sel_counts + (size_t)(slot0 + k) * ctx->n_sms;
         pb.cutoff_out = ctx->cutoff + slot0 + k;
-        pb.cutoff_hint = ctx->prefetch ? w->hint : nullptr;
+        pb.cutoff_hint = ctx->use_hint ? w->hint : nullptr;
+        pb.rounds_out = (slot0 + k == 0) ? ctx->loops : nullptr;
         pb.err_flag = ctx->v2_err;
         pb.trace = ctx->trace;
         pb.in = w->in; pb.C = w->C; pb.P = w->P; pb.q = effort_q(c.effort, w->n_probes); pb.layout = w->layout;
@@ -534,6 +539,7 @@ static int launch_v2_batch(effort_ctx* ctx, const V2Call* calls, int n, int slot
     batch.list_cap = (list_cap + 63) & ~63;
     using L = V2Smem<SLOTS, VEC>;
     batch.dynamic = ctx->dynamic;
+    batch.prefetch = ctx->prefetch;
     const size_t smem = L::bytes(batch.list_cap, D);
     if (smem > kMaxSmem) return EFFORT_ESHAPE;
     // every kernel needs its own opt-in to > 48 KB of dynamic shared memory (per device): keyed by the function pointer

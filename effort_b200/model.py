@@ -184,7 +184,7 @@ class DecodeModel:
             m.set_layer(i, make(cfg.dim, cfg.dim), make(kvd, cfg.dim), make(kvd, cfg.dim), make(cfg.dim, cfg.dim),
                         make(cfg.hidden_dim, cfg.dim, n_experts), make(cfg.dim, cfg.hidden_dim, n_experts),
                         make(cfg.hidden_dim, cfg.dim, n_experts), norm_vec(), norm_vec())
-            m.set_moe(i, _rand_w(n_experts, cfg.dim, gen, scale=0.5))
+            m.set_moe(i, _rand_w(n_experts, cfg.dim, gen, scale=0.02))   # logits ~ N(0, 1.3^2): exp() stays finite
         m.set_head(norm_vec(), _rand_w(cfg.vocab, cfg.dim, gen), _rand_w(cfg.vocab, cfg.dim, gen, scale=1.0))
         torch.cuda.synchronize()
         return m
