@@ -31,7 +31,7 @@ struct __align__(16) V4Desc {
     uint32_t off;      // byte offset of the unit's first row in the pair's ring
     uint32_t n;        // rows (0 = stop marker)
     float val;         // the input's multiplier
-    uint32_t rstride;  // bytes between the unit's rows in the ring
+    uint32_t charged;  // ring bytes the unit holds (incl. a wrap skip charged to it): what the producer takes back
 };
 
 struct V4Header {
@@ -40,11 +40,11 @@ struct V4Header {
     float red[kV4SelWarps];
     float cutoff, denom;
     int sel_rows;
-    unsigned ticket;                     // next input a producer may take
+    unsigned ticket;                     // next unit of the list a producer may take
+    unsigned n_units;                    // units in the list
     unsigned long long full_bar[kV4Pairs][kV4Units];
     unsigned long long empty_bar[kV4Pairs][kV4Units];
     V4Desc desc[kV4Pairs][kV4Units];
-    uint16_t usize[kV4Pairs][kV4Units];  // ring bytes / 16 a unit holds (incl. a wrap skip charged to it)
 };
 
 struct V4Smem {
@@ -52,7 +52,7 @@ struct V4Smem {
     static constexpr int kTileBytes = kTileFloats * 4;
     static constexpr size_t kHdrBytes = (sizeof(V4Header) + 127) & ~size_t(127);
     static constexpr size_t kBytes = (size_t)kTileBytes /*alignment slack*/ + (size_t)kV4Pairs * kTileBytes + kHdrBytes +
-                                     (size_t)kV2MaxInputs * (4 + 4 + 4) + 128 + (size_t)kV4Pairs * kV4RingBytes;
+                                     (size_t)kV2MaxInputs * 16 + 128 + (size_t)kV4Pairs * kV4RingBytes;
 };
 
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
@@ -63,9 +63,9 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
 // slots the accumulating warps need; returns false after ~1 s (a bug, never a data condition)
 __device__ __forceinline__ bool mbar_wait_parked(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    for (int tries = 0; tries < (1 << 19) && !done; tries++) {
+    for (int tries = 0; tries < (1 << 22) && !done; tries++) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done) : "r"(bar), "r"(parity), "r"(2000u) : "memory");
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(200u) : "memory");
     }
     return done != 0;
 }
@@ -137,7 +137,7 @@ __device__ __forceinline__ float select_cutoff_group(const uint32_t (&keys)[16],
     return __uint_as_float((uint32_t)(L + 1) << 16);
 }
 
-template <int CUT>
+template <int CUT, bool BULK>
 __global__ void __launch_bounds__(kV2Threads, 1)
 bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -167,12 +167,8 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
     p += (size_t)NC * V4Smem::kTileBytes;
     V4Header& hdr = *reinterpret_cast<V4Header*>(p);
     p += V4Smem::kHdrBytes;
-    uint32_t* sbase = reinterpret_cast<uint32_t*>(p);
-    p += (size_t)kV2MaxInputs * 4;
-    float* sval = reinterpret_cast<float*>(p);
-    p += (size_t)kV2MaxInputs * 4;
-    uint32_t* smask = reinterpret_cast<uint32_t*>(p);
-    p += (size_t)kV2MaxInputs * 4;
+    uint4* ulist = reinterpret_cast<uint4*>(p);  // the pass's units: {first 16-byte piece, rows, multiplier bits, -}
+    p += (size_t)kV2MaxInputs * 16;
     p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 127) & ~uintptr_t(127));
     float* ring_f = reinterpret_cast<float*>(p);
     const uint32_t ring_saddr = (uint32_t)__cvta_generic_to_shared(p) + (uint32_t)pair * (uint32_t)kV4RingBytes;
@@ -221,10 +217,11 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
     }
     if (warp == NC) {  // first producer warp: the ring barriers
         for (int s = lane; s < NC * kV4Units; s += 32) {
-            mbar_init((uint32_t)__cvta_generic_to_shared(&hdr.full_bar[0][0] + s), 33);  // 32 cp.async arrivals + the header's
+            // LDGSTS: 32 cp.async arrivals + the descriptor's; bulk copy: the expect_tx arrival (bytes complete the phase)
+            mbar_init((uint32_t)__cvta_generic_to_shared(&hdr.full_bar[0][0] + s), BULK ? 1 : 33);
             mbar_init((uint32_t)__cvta_generic_to_shared(&hdr.empty_bar[0][0] + s), 1);
         }
-        if (lane == 0) { hdr.ticket = 0u; hdr.sel_rows = 0; }
+        if (lane == 0) { hdr.ticket = 0u; hdr.n_units = 0u; hdr.sel_rows = 0; }
         // (the __syncthreads before the first use orders the initialisation: no cluster, no async-proxy user here)
     }
     V2_TRACE(1);
@@ -402,9 +399,16 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
     const uint4* bk16 = reinterpret_cast<const uint4*>(pb.bk + (size_t)pb.in * P * ((size_t)slice * pb.W));  // slice-major
     const uint32_t rs16 = (uint32_t)(seg_bytes >> 4);
 
+    // debugging aid (EFFORT_TRACE): issue / arrival / release times of the first 80 units of pair 0 of CTA 0
+    unsigned long long* utrace = (pb.trace && blockIdx.x == 0 && pair == 0) ? pb.trace + (size_t)kNumSMs * 16 : nullptr;
     // pair state.  Both sides count units (seq); unit s uses descriptor slot s % kV4Units, barrier phase (s / kV4Units) & 1.
     // Producer only: ring head, free bytes, oldest unit not yet reclaimed.
     uint32_t seq = 0, tail_seq = 0, head = 0, free_b = kV4RingBytes;
+    const uint32_t ticket_saddr = (uint32_t)__cvta_generic_to_shared(&hdr.ticket);
+    const uint32_t full0 = (uint32_t)__cvta_generic_to_shared(&hdr.full_bar[pair][0]);
+    const uint32_t empty0 = (uint32_t)__cvta_generic_to_shared(&hdr.empty_bar[pair][0]);
+    const uint32_t desc0 = (uint32_t)__cvta_generic_to_shared(&hdr.desc[pair][0]);
+    bool pristine = true;  // ticket / n_units still at their initial zero
     // ---- passes over the inputs of this row split (one pass for every Mistral shape) ----
     for (int j0 = 0; j0 < n_in; j0 += NT) {
         const int j = j0 + tid;
@@ -420,122 +424,154 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                 if (vmode == kVNorm) my_v = (my_v / denom) * __half2float(pb.norm_w[i]);
                 else if (vmode == kVSilu) my_v = silu_mul(my_v, pb.v2[i]);
             }
-            if (tid == 0) hdr.ticket = 0u;
         }
         // 2. selection mask of this thread's input (prepareDispatch, bucketMul.metal:66)
-        unsigned mask = 0u;
+        unsigned m = 0u;
 #pragma unroll
         for (int rho = 0; rho < 16; rho++)
-            if (rho < P && j < n_in && row_selected(cutoff, sel_stat[rho], my_v)) mask |= 1u << rho;
-        smask[tid] = mask;
-        if (j < n_in) {
-            const int i = rsp + j * RS;
-            sbase[tid] = (uint32_t)(((size_t)e_no * pb.in * P * C + (size_t)i * P * slice_cols) >> 3);
-            sval[tid] = pb.out_scale ? my_v * *pb.out_scale : my_v;  // the selection above used the unscaled input
+            if (rho < P && j < n_in && row_selected(cutoff, sel_stat[rho], my_v)) m |= 1u << rho;
+        if (pb.sel_counts) {
+            const int wrows = __reduce_add_sync(0xffffffffu, __popc(m));
+            if (lane == 0 && wrows) atomicAdd(&hdr.sel_rows, wrows);
         }
-        const int wrows = __reduce_add_sync(0xffffffffu, __popc(mask));
-        if (lane == 0 && wrows) atomicAdd(&hdr.sel_rows, wrows);
-        __syncthreads();
-        V2_TRACE(8);
-
-        const int n_pass = min(NT, n_in - j0);
-        if (!consumer) {
-            // ---- 3a. producer of pair `pair`: the next input nobody has taken, its selected runs into the ring ----
-            const uint32_t ticket_saddr = (uint32_t)__cvta_generic_to_shared(&hdr.ticket);
-            auto reclaim = [&]() {  // wait for the consumer to release the oldest unit, take its bytes back
-                const uint32_t ts = tail_seq & (kV4Units - 1);
-                if (!mbar_wait_parked((uint32_t)__cvta_generic_to_shared(&hdr.empty_bar[pair][ts]), (tail_seq / kV4Units) & 1u)) {
-                    if (pb.err_flag && lane == 0) atomicExch(pb.err_flag, 3u);
-                }
-                free_b += (uint32_t)hdr.usize[pair][ts] * 16u;
-                tail_seq++;
-            };
-            auto fill = [&](uint32_t src16, int len, float val) {  // len rows (0 = stop marker) as the next unit
-                const uint32_t bytes = (uint32_t)(len * seg_bytes);
-                const uint32_t skip = (head + bytes > (uint32_t)kV4RingBytes) ? ((uint32_t)kV4RingBytes - head) : 0u;
-                while (free_b < bytes + skip || seq - tail_seq >= (uint32_t)kV4Units) reclaim();
-                const uint32_t off = skip ? 0u : head;
-                const uint32_t slot = seq & (kV4Units - 1);
-                const uint32_t sa = ring_saddr + off;
-                const int pieces = len * (int)rs16;
-                const uint4* src = bk16 + src16;
-                for (int q = lane; q < pieces; q += 32) cp_async16(sa + (uint32_t)q * 16u, src + q, pol);
-                if (lane == 0) {
-                    hdr.usize[pair][slot] = (uint16_t)((bytes + skip) >> 4);
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"((uint32_t)__cvta_generic_to_shared(&hdr.desc[pair][slot])),
-                                 "r"(off), "r"((uint32_t)len), "r"(__float_as_uint(val)), "r"((uint32_t)seg_bytes) : "memory");
-                }
-                const uint32_t fb = (uint32_t)__cvta_generic_to_shared(&hdr.full_bar[pair][slot]);
-                cp_async_arrive_noinc(fb);  // arrives when this lane's copies have landed
-                __syncwarp();
-                if (lane == 0) mbar_arrive(fb);  // releases the descriptor
-                seq++;
-                head = off + bytes;
-                free_b -= bytes + skip;
-                if (head >= (uint32_t)kV4RingBytes) head = 0u;
-            };
-#pragma unroll 1
-            for (;;) {
-                uint32_t jj = 0;
-                if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(jj) : "r"(ticket_saddr) : "memory");
-                jj = __shfl_sync(0xffffffffu, jj, 0);
-                if ((int)jj >= n_pass) break;
-                unsigned m = smask[jj];
-                if (!m) continue;
-                const uint32_t sb = sbase[jj];
-                const float sv = sval[jj];
-                while (m) {  // maximal runs of selected ranks: one unit each (a prefix of the ranks in the normal case)
+        const uint32_t my_src = (uint32_t)(((size_t)e_no * pb.in * P * C + (size_t)(rsp + j * RS) * P * slice_cols) >> 3);
+        const float my_val = pb.out_scale ? my_v * *pb.out_scale : my_v;  // the selection above used the unscaled input
+        // ---- rounds: every input contributes its next maximal run of selected ranks as one unit.  Bucket statistics fall
+        // with the rank, so a mask is a prefix of the ranks and one round is the normal case; arbitrary statistics (tests)
+        // take one round per run. ----
+        bool more;
+        do {
+            if (!pristine) {
+                __syncthreads();
+                if (tid == 0) { hdr.ticket = 0u; hdr.n_units = 0u; }
+                __syncthreads();
+            }
+            pristine = false;
+            {   // 2b. the unit list: order is irrelevant, so a warp reserves its records with one shared-memory atomic
+                const unsigned bal = __ballot_sync(0xffffffffu, m != 0u);
+                unsigned base = 0u;
+                if (lane == 0 && bal) base = atomicAdd(&hdr.n_units, (unsigned)__popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (m) {
                     const int st = __ffs((int)m) - 1;
                     const int len = __ffs((int)~(m >> st)) - 1;
                     m &= ~(((1u << len) - 1u) << st);
-                    fill(sb + (uint32_t)st * rs16, len, sv);
+                    ulist[base + (unsigned)__popc(bal & ((1u << lane) - 1u))] =
+                        make_uint4(my_src + (uint32_t)st * rs16, (uint32_t)len, __float_as_uint(my_val), 0u);
                 }
             }
-            fill(0u, 0, 0.f);  // stop marker for the consumer
-        } else {
-            // ---- 3b. consumer ----
+            more = __syncthreads_or(m != 0u) != 0;
+            V2_TRACE(8);
+
+            if (!consumer) {
+                // ---- 3a. producer of pair `pair`: the next unit nobody has taken goes into the pair's ring ----
+                const uint32_t nu = hdr.n_units;
+                auto grab = [&]() {
+                    uint32_t t = 0u;
+                    if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(t) : "r"(ticket_saddr) : "memory");
+                    return t;
+                };
+                auto reclaim = [&]() {  // wait for the consumer to release the oldest unit, take its bytes back
+                    const uint32_t ts = tail_seq & (kV4Units - 1);
+                    if (!mbar_wait_parked(empty0 + ts * 8u, (tail_seq / kV4Units) & 1u)) {
+                        if (pb.err_flag && lane == 0) atomicExch(pb.err_flag, 3u);
+                    }
+                    free_b += hdr.desc[pair][ts].charged;
+                    tail_seq++;
+                };
+                auto fill = [&](uint32_t src16, uint32_t len, uint32_t valbits) {  // len rows (0 = stop marker) as the next unit
+                    const uint32_t bytes = len * (uint32_t)seg_bytes;
+                    const uint32_t skip = (head + bytes > (uint32_t)kV4RingBytes) ? ((uint32_t)kV4RingBytes - head) : 0u;
+                    while (free_b < bytes + skip || seq - tail_seq >= (uint32_t)kV4Units) reclaim();
+                    const uint32_t off = skip ? 0u : head;
+                    const uint32_t slot = seq & (kV4Units - 1);
+                    const uint32_t sa = ring_saddr + off;
+                    const uint32_t fb = full0 + slot * 8u;
+                    const uint4* src = bk16 + src16;
+                    if (lane == 0)
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(desc0 + slot * 16u), "r"(off), "r"(len), "r"(valbits),
+                                     "r"(bytes + skip) : "memory");
+                    if (utrace && lane == 0 && seq < 80u) { utrace[4 * seq] = gtime_ns(); utrace[4 * seq + 3] = (unsigned long long)len; }
+                    if constexpr (BULK) {
+                        // one bulk copy per unit (slice-major: the run is contiguous); its bytes complete the phase
+                        if (lane == 0) {
+                            if (bytes) {
+                                mbar_expect_tx(fb, (int)bytes);
+                                bulk_g2s(sa, src, (int)bytes, fb, pol);
+                            } else {
+                                mbar_arrive(fb);
+                            }
+                        }
+                    } else {
+                        const uint32_t pieces = len * rs16;
+                        const uint32_t d0 = sa + (uint32_t)lane * 16u;
+                        const uint4* s0p = src + lane;
+                        for (uint32_t q = (uint32_t)lane; q < pieces; q += 32u) cp_async16(d0 + (q - (uint32_t)lane) * 16u, s0p + (q - (uint32_t)lane), pol);
+                        cp_async_arrive_noinc(fb);  // arrives when this lane's copies have landed
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(fb);  // releases the descriptor
+                    }
+                    seq++;
+                    head = off + bytes;
+                    free_b -= bytes + skip;
+                    if (head >= (uint32_t)kV4RingBytes) head = 0u;
+                };
+                uint32_t tk = grab();
 #pragma unroll 1
-            for (;;) {
-                const uint32_t slot = seq & (kV4Units - 1);
-                if (!mbar_wait_parked((uint32_t)__cvta_generic_to_shared(&hdr.full_bar[pair][slot]), (seq / kV4Units) & 1u)) {
-                    if (pb.err_flag && lane == 0) atomicExch(pb.err_flag, 2u);
-                    break;
+                for (;;) {
+                    const uint32_t t = __shfl_sync(0xffffffffu, tk, 0);
+                    if (t >= nu) break;
+                    const uint4 rec = ulist[t];
+                    tk = grab();  // the next ticket travels while this unit is issued
+                    fill(rec.x, rec.y, rec.z);
                 }
-                seq++;
-                uint32_t hoff, hn, hv, hs;
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hoff), "=r"(hn), "=r"(hv), "=r"(hs)
-                             : "r"((uint32_t)__cvta_generic_to_shared(&hdr.desc[pair][slot])));
-                const int n = (int)hn;
-                const uint32_t eb = (uint32_t)__cvta_generic_to_shared(&hdr.empty_bar[pair][slot]);
-                if (n == 0) {
+                fill(0u, 0u, 0u);  // stop marker for the consumer
+            } else {
+                // ---- 3b. consumer ----
+#pragma unroll 1
+                for (;;) {
+                    const uint32_t slot = seq & (kV4Units - 1);
+                    if (!mbar_wait(full0 + slot * 8u, (seq / kV4Units) & 1u)) {
+                        if (pb.err_flag && lane == 0) atomicExch(pb.err_flag, 2u);
+                        break;
+                    }
+                    if (utrace && lane == 0 && seq < 80u) utrace[4 * seq + 1] = gtime_ns();
+                    seq++;
+                    uint32_t hoff, hn, hv, hs;
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hoff), "=r"(hn), "=r"(hv), "=r"(hs) : "r"(desc0 + slot * 16u));
+                    const int n = (int)hn;
+                    const uint32_t eb = empty0 + slot * 8u;
+                    if (n == 0) {
+                        if (lane == 0) mbar_arrive(eb);
+                        break;
+                    }
+                    const float val = __uint_as_float(hv);
+                    const uint32_t sa = ring_saddr + hoff;
+                    if (full_width) {
+                        uint32_t a0 = sa + (uint32_t)(lane * LB);
+                        int r = 0;
+                        for (; r + 4 <= n; r += 4, a0 += 4 * kRow) accumulate_unit_fp16<VEC, 4, kRow>(base_lane, val, a0);
+                        switch (n - r) {
+                            case 1: accumulate_unit_fp16<VEC, 1, kRow>(base_lane, val, a0); break;
+                            case 2: accumulate_unit_fp16<VEC, 2, kRow>(base_lane, val, a0); break;
+                            case 3: accumulate_unit_fp16<VEC, 3, kRow>(base_lane, val, a0); break;
+                            default: break;
+                        }
+                    } else {  // narrow slice: rows are seg_bytes apart, R rows per step, lanes past the slice idle
+                        for (int st = 0; st * R < n; st++) {
+                            const int r = st * R + rowslot;
+                            const bool ok = (rowslot < R) && (r < n) && col_ok;
+                            uint32_t ww[2] = {0u, 0u};
+                            if (ok) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(ww[0]), "=r"(ww[1]) : "r"(sa + (uint32_t)(r * seg_bytes + lcol * LB)));
+                            accumulate_words<SLOTS, VEC>(base_lane, ok ? val : 0.f, ww);
+                        }
+                    }
+                    __syncwarp();  // every lane has read the unit's bytes
                     if (lane == 0) mbar_arrive(eb);
-                    break;
+                    if (utrace && lane == 0 && seq <= 80u) utrace[4 * (seq - 1) + 2] = gtime_ns();
                 }
-                const float val = __uint_as_float(hv);
-                const uint32_t sa = ring_saddr + hoff;
-                if (full_width) {
-                    uint32_t a0 = sa + (uint32_t)(lane * LB);
-                    int r = 0;
-                    for (; r + 4 <= n; r += 4, a0 += 4 * kRow) accumulate_unit_fp16<VEC, 4, kRow>(base_lane, val, a0);
-                    switch (n - r) {
-                        case 1: accumulate_unit_fp16<VEC, 1, kRow>(base_lane, val, a0); break;
-                        case 2: accumulate_unit_fp16<VEC, 2, kRow>(base_lane, val, a0); break;
-                        case 3: accumulate_unit_fp16<VEC, 3, kRow>(base_lane, val, a0); break;
-                        default: break;
-                    }
-                } else {  // narrow slice: rows are seg_bytes apart, R rows per step, lanes past the slice idle
-                    for (int st = 0; st * R < n; st++) {
-                        const int r = st * R + rowslot;
-                        const bool ok = (rowslot < R) && (r < n) && col_ok;
-                        uint32_t ww[2] = {0u, 0u};
-                        if (ok) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(ww[0]), "=r"(ww[1]) : "r"(sa + (uint32_t)(r * seg_bytes + lcol * LB)));
-                        accumulate_words<SLOTS, VEC>(base_lane, ok ? val : 0.f, ww);
-                    }
-                }
-                __syncwarp();  // every lane has read the unit's bytes
-                if (lane == 0) mbar_arrive(eb);
             }
-        }
+        } while (more);
     }
     __syncthreads();
     if (pb.sel_counts && slice == 0 && tid == 0) pb.sel_counts[rsp] = (uint32_t)hdr.sel_rows;

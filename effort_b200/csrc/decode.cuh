@@ -215,14 +215,16 @@ argmax_advance_kernel(const float* __restrict__ logits, int n, int* __restrict__
 // warp per expert (n_experts <= 8 per pass).  The indices stay on the device: the expert GEMVs read them as `expNo`.
 __global__ void __launch_bounds__(256)
 moe_gate_kernel(const float* __restrict__ h, const __half* __restrict__ norm_w, float eps, const __half* __restrict__ gate,
-                int n_experts, int dim, uint32_t* __restrict__ gate_idx, float* __restrict__ gate_val) {
+                int n_experts, int dim, uint32_t* __restrict__ gate_idx, float* __restrict__ gate_val, float* __restrict__ h_keep) {
     __shared__ float red[8];
     __shared__ float logit[64];
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float ss = 0.f;
-    for (int i = threadIdx.x; i < dim; i += blockDim.x) { const float x = h[i]; ss += x * x; }
+    // both routed experts normalise the SAME hidden state (fxn is computed once, runNetwork.swift:176), but the first
+    // expert's w2 already adds into h: keep a copy for the expert GEMVs to read
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) { const float x = h[i]; ss += x * x; h_keep[i] = x; }
     ss = warp_sum_f(ss);
     if (lane == 0) red[warp] = ss;
     __syncthreads();

@@ -154,14 +154,14 @@ extern "C" int effort_ctx_create(int device, effort_ctx_t** ctx_out) {
     CK(cudaMemset(c->sel_counts, 0, sizeof(uint32_t) * kMaxBatch * c->n_sms));
     c->sel_cap = (size_t)kMaxBatch * c->n_sms;
     { const char* e = getenv("EFFORT_CUTOFF"); if (e && !strcmp(e, "bisect")) c->cutoff_mode = 1; }
-    { const char* e = getenv("EFFORT_STAGE"); if (e) c->stage_mode = !strcmp(e, "ldgsts") ? 0 : !strcmp(e, "tma") ? 2 : 3; }
+    { const char* e = getenv("EFFORT_STAGE"); if (e) c->stage_mode = !strcmp(e, "ldgsts") ? 0 : !strcmp(e, "tma") ? 2 : !strcmp(e, "bulk") ? 4 : 3; }
     { const char* e = getenv("EFFORT_ENGINE"); if (e && atoi(e) == 1) c->engine = 1; }
     { const char* e = getenv("EFFORT_DYN"); if (e) c->dynamic = atoi(e) ? 1 : 0; }
     { const char* e = getenv("EFFORT_PREFETCH"); if (e) c->prefetch = atoi(e) ? 1 : 0; }
     { const char* e = getenv("EFFORT_HINT"); if (e) c->use_hint = atoi(e) ? 1 : 0; }
     if (getenv("EFFORT_TRACE")) {
-        CK(cudaMalloc(&c->trace, sizeof(unsigned long long) * 16 * c->n_sms));
-        CK(cudaMemset(c->trace, 0, sizeof(unsigned long long) * 16 * c->n_sms));
+        CK(cudaMalloc(&c->trace, sizeof(unsigned long long) * (16 * c->n_sms + 4 * 80)));
+        CK(cudaMemset(c->trace, 0, sizeof(unsigned long long) * (16 * c->n_sms + 4 * 80)));
     }
     *ctx_out = c;
     return EFFORT_OK;
@@ -176,7 +176,7 @@ extern "C" int effort_ctx_set_cutoff_mode(effort_ctx_t* c, int mode) {
 extern "C" int effort_ctx_set_option(effort_ctx_t* c, const char* name, int value) {
     if (!c || !name) return EFFORT_EINVAL;
     if (!strcmp(name, "engine")) { if (value != 1 && value != 2) return EFFORT_EINVAL; c->engine = value; return EFFORT_OK; }
-    if (!strcmp(name, "stage")) { if (value != 0 && value != 2 && value != 3) return EFFORT_EINVAL; c->stage_mode = value; return EFFORT_OK; }
+    if (!strcmp(name, "stage")) { if (value != 0 && value != 2 && value != 3 && value != 4) return EFFORT_EINVAL; c->stage_mode = value; return EFFORT_OK; }
     if (!strcmp(name, "hint")) { if (value != 0 && value != 1) return EFFORT_EINVAL; c->use_hint = value; return EFFORT_OK; }
     if (!strcmp(name, "prefetch")) { if (value != 0 && value != 1) return EFFORT_EINVAL; c->prefetch = value; return EFFORT_OK; }
     if (!strcmp(name, "dynamic")) { if (value != 0 && value != 1) return EFFORT_EINVAL; c->dynamic = value; return EFFORT_OK; }
@@ -192,6 +192,14 @@ extern "C" int effort_ctx_error_flag(effort_ctx_t* c, unsigned* flag_out, void* 
 
 // debugging aid (not part of the public header): copies the [n_sms][8] phase timestamps of the last fused
 // launch; returns the number of CTAs rows or <0.
+extern "C" int effort_debug_read_unit_trace(effort_ctx_t* c, unsigned long long* host320) {
+    if (!c || !c->trace || !host320) return EFFORT_EINVAL;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(host320, c->trace + 16 * c->n_sms, sizeof(unsigned long long) * 320, cudaMemcpyDeviceToHost));
+    CK(cudaMemset(c->trace + 16 * c->n_sms, 0, sizeof(unsigned long long) * 320));
+    return EFFORT_OK;
+}
+
 extern "C" int effort_debug_read_trace(effort_ctx_t* c, unsigned long long* host, int max_rows) {
     if (!c || !c->trace || !host) return EFFORT_EINVAL;
     CK(cudaDeviceSynchronize());
@@ -559,8 +567,13 @@ static int launch_v2_batch(effort_ctx* ctx, const V2Call* calls, int n, int slot
     bool all_slice = true;
     for (int k = 0; k < n; k++) all_slice = all_slice && calls[k].w->layout == kSliceMajor;
     if (SLOTS == 16 && all_slice && ctx->stage_mode == 3) {
-        // consumer / producer warp pairs with private rings (bucket_mul_v4.cuh): the default path
-        rc = bisect ? go(bucket_mul_v4_kernel<kCutBisect>, kV2Threads, V4Smem::kBytes) : go(bucket_mul_v4_kernel<kCutSelect>, kV2Threads, V4Smem::kBytes);
+        // consumer / producer warp pairs with private rings (bucket_mul_v4.cuh), 16-byte cp.async per lane: the default path
+        rc = bisect ? go(bucket_mul_v4_kernel<kCutBisect, false>, kV2Threads, V4Smem::kBytes)
+                    : go(bucket_mul_v4_kernel<kCutSelect, false>, kV2Threads, V4Smem::kBytes);
+    } else if (SLOTS == 16 && all_slice && ctx->stage_mode == 4) {
+        // the same pairs, one bulk copy (TMA) per unit
+        rc = bisect ? go(bucket_mul_v4_kernel<kCutBisect, true>, kV2Threads, V4Smem::kBytes)
+                    : go(bucket_mul_v4_kernel<kCutSelect, true>, kV2Threads, V4Smem::kBytes);
     } else if (SLOTS == 16 && all_slice && ctx->stage_mode == 2) {
         // TMA pipeline: producer warp + byte ring (bucket_mul_v3.cuh)
         batch.ring_bytes = (int)((kMaxSmem - V3Smem::kFixed) & ~(size_t)255);
@@ -1178,6 +1191,7 @@ struct effort_model {
     float *x1_2[2] = {nullptr, nullptr}, *x3_2[2] = {nullptr, nullptr};
     uint32_t* gate_idx = nullptr;  // MoE: the two routed experts of the current layer (device, read as expNo)
     float* gate_val = nullptr;     // MoE: their softmax weights
+    float* h_keep = nullptr;       // MoE: the hidden state both routed experts normalise (h itself takes the first one's output)
     float2* head_cand = nullptr;   // per-CTA argmax candidates of head_kernel
     unsigned* head_ticket = nullptr;
     int host_pos = 0;              // tokens decoded since the last reset (bounds the KV cache)
@@ -1243,7 +1257,8 @@ extern "C" int effort_model_create(effort_ctx_t* ctx, const effort_model_config_
             return rc;
     }
     if ((rc = model_alloc(m, m->head_cand, (size_t)ctx->n_sms * 8)) || (rc = model_alloc(m, m->head_ticket, 1)) ||
-        (rc = model_alloc(m, m->gate_idx, 2)) || (rc = model_alloc(m, m->gate_val, 2)))
+        (rc = model_alloc(m, m->gate_idx, 2)) || (rc = model_alloc(m, m->gate_val, 2)) ||
+        (rc = model_alloc(m, m->h_keep, (size_t)cfg->dim)))
         return rc;
     CK(cudaMallocHost(&m->h_token, sizeof(int)));
     CK(cudaMallocHost(&m->h_next, sizeof(int)));
@@ -1418,7 +1433,7 @@ static int model_enqueue_token_v2(effort_model* m, double effort, cudaStream_t s
         const int n_routed = l.gate ? 2 : 1;  // MoE: the two experts the gate picks (runNetwork.swift:185-200)
         if (l.gate) {
             CK(launch_pdl(moe_gate_kernel, dim3(1), dim3(256), 0, s, (const float*)m->h, l.ffn_norm, c.norm_eps, l.gate, l.n_experts,
-                          c.dim, m->gate_idx, m->gate_val));
+                          c.dim, m->gate_idx, m->gate_val, m->h_keep));
             LAUNCHED();
         }
         for (int r = 0; r < n_routed; r++) {
@@ -1426,7 +1441,7 @@ static int model_enqueue_token_v2(effort_model* m, double effort, cudaStream_t s
             const effort_weights* ww[2] = {l.w1, l.w3};
             float* o13[2] = {m->x1_2[b], m->x3_2[b]};
             for (int k = 0; k < 2; k++) {
-                w13[k].v = m->h; w13[k].norm_w = l.ffn_norm; w13[k].norm_eps = c.norm_eps; w13[k].w = ww[k];
+                w13[k].v = l.gate ? m->h_keep : m->h; w13[k].norm_w = l.ffn_norm; w13[k].norm_eps = c.norm_eps; w13[k].w = ww[k];
                 w13[k].out = o13[k]; w13[k].effort = effort;
                 // dense layers accumulate into buffers an earlier kernel cleared; a routed expert overwrites (the second
                 // expert reuses the buffers of the first)

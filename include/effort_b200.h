@@ -88,7 +88,7 @@ int effort_ctx_set_cutoff_mode(effort_ctx_t* ctx, int mode);
  *              1 round-1 kernel + integrate launch (deterministic fp32 order)
  *   "stage"    3 (default) eight consumer warps accumulate, eight producer warps stage whole-input units (1..16 rows)
  *              with cp.async into per-pair rings and hand them over through mbarriers (slice-major FP16 weights; other
- *              weights take stage 0); 2 one TMA (cp.async.bulk) producer warp, a shared byte ring and 16 consumers
+ *              weights take stage 0); 4 the same pairs with one bulk copy (cp.async.bulk) per unit; 2 one TMA (cp.async.bulk) producer warp, a shared byte ring and 16 consumers
  *              (slice-major FP16 weights; measured slower: the single producer's serial issue is the limit);
  *              0 sixteen self-serving warps with private cp.async rings, units of at most 4 rows
  *   "dynamic"  per-warp rings (stage 0/1) only: 0 (default) static round robin of the units, 1 units from a shared counter
@@ -96,7 +96,7 @@ int effort_ctx_set_cutoff_mode(effort_ctx_t* ctx, int mode);
  *              previous call (3 rounds instead of 8 when it moved by less than 12 %; the result never depends on it)
  *   "prefetch" 0 (default) / 1 stage 3 only: while the cutoff is being computed, rows that the matrix's previous cutoff
  *              would select are prefetched into L2 (measured: no gain -- the gather is not DRAM-latency bound)
- * Returns EFFORT_EINVAL for an unknown name or value.  Environment defaults: EFFORT_ENGINE, EFFORT_STAGE=bulk,
+ * Returns EFFORT_EINVAL for an unknown name or value.  Environment defaults: EFFORT_ENGINE, EFFORT_STAGE (ldgsts|tma|bulk),
  * EFFORT_DYN, EFFORT_PREFETCH, EFFORT_HINT. */
 int effort_ctx_set_option(effort_ctx_t* ctx, const char* name, int value);
 /* Non-zero once a fused kernel of this context gave up waiting for a co-resident CTA (2 s): its output is invalid.

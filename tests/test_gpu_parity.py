@@ -256,7 +256,7 @@ def test_no_repack_layout_same_selection_and_sum(T, ops):
 
 
 @pytest.mark.parametrize("in_dim,out_dim", [(4096, 4096), (4096, 1024), (4096, 11008), (14336, 4096)])
-@pytest.mark.parametrize("stage,flags", [(0, 2), (2, 2), (3, 2), (0, 4), (3, 4)])
+@pytest.mark.parametrize("stage,flags", [(0, 2), (2, 2), (3, 2), (4, 2), (0, 4), (3, 4)])
 def test_layouts_and_bulk_stage(T, ops, mode, in_dim, out_dim, stage, flags):
     """device layouts (2 = slice-major: contiguous row sets per column slice, the default; 4 = input-major) x staging
     (3 = consumer/producer warp pairs, the default; 2 = one TMA producer warp + byte ring; 0 = self-serving warps with

@@ -20,6 +20,8 @@ ctx = ops.default_context()
 L = _lib.load()
 L.effort_debug_read_trace.restype = C.c_int
 L.effort_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+L.effort_debug_read_unit_trace.restype = C.c_int
+L.effort_debug_read_unit_trace.argtypes = [C.c_void_p, C.c_void_p]
 for k in range(200):
     ops.bucketMul(v, ws[k % 4], None, out, a.effort)
 torch.cuda.synchronize()
@@ -39,3 +41,12 @@ for rep in range(3):
     for k, nm in names.items():
         rel = (t[:, k] - t0) / 1000.0
         print(f"   {nm:10s} min {rel.min():7.2f}  median {np.median(rel):7.2f}  max {rel.max():7.2f} us")
+    ub = np.zeros((80, 4), dtype=np.uint64)
+    if L.effort_debug_read_unit_trace(ctx._h, ub.ctypes.data) == 0 and rep == 2:
+        u = ub.astype(np.int64)
+        print("   units of pair 0, CTA 0 (us from the CTA's start): rows, copies issued, data seen by the consumer, released")
+        for k in range(80):
+            if u[k, 0] == 0:
+                break
+            print(f"     unit {k:2d}: {int(u[k,3]):2d} rows  issued {(u[k,0]-t[0,0])/1000.0:6.2f}  arrived {(u[k,1]-t[0,0])/1000.0:6.2f}  "
+                  f"released {(u[k,2]-t[0,0])/1000.0:6.2f}")
