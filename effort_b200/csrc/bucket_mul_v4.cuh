@@ -52,7 +52,8 @@ struct V4Smem {
     static constexpr int kTileBytes = kTileFloats * 4;
     static constexpr size_t kHdrBytes = (sizeof(V4Header) + 127) & ~size_t(127);
     static constexpr size_t kBytes = (size_t)kTileBytes /*alignment slack*/ + (size_t)kV4Pairs * kTileBytes + kHdrBytes +
-                                     (size_t)kV2MaxInputs * 16 + 128 + (size_t)kV4Pairs * kV4RingBytes;
+                                     (size_t)kV2MaxInputs * 16 + 128 + (size_t)kV4Pairs * kV4RingBytes +
+                                     1024 /* the consumers read (and ignore) up to three rows past a unit's end */;
 };
 
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
@@ -67,6 +68,14 @@ __device__ __forceinline__ bool mbar_wait_parked(uint32_t bar, uint32_t parity) 
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done) : "r"(bar), "r"(parity), "r"(200u) : "memory");
     }
+    return done != 0;
+}
+
+// non-blocking phase test
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done != 0;
 }
 
@@ -135,6 +144,23 @@ __device__ __forceinline__ float select_cutoff_group(const uint32_t (&keys)[16],
     }
     if (rounds_out && gt == 0) *rounds_out = round;
     return __uint_as_float((uint32_t)(L + 1) << 16);
+}
+
+// the read-modify-writes of N rows whose staged words are already in registers (cf. accumulate_unit_fp16)
+template <int VEC, int N>
+__device__ __forceinline__ void accumulate_rows_fp16(uint32_t base_lane, float val, const uint32_t (&w)[4][2]) {
+    uint32_t a[N][VEC];
+    float f[N][VEC], acc[N][VEC];
+#pragma unroll
+    for (int r = 0; r < N; r++) AccFp16<VEC, 0>::addr(w[r], base_lane, a[r], f[r]);
+#pragma unroll
+    for (int r = 0; r < N; r++) RmwFp16<VEC, 0>::load(a[r], acc[r]);
+#pragma unroll
+    for (int r = 0; r < N; r++)
+#pragma unroll
+        for (int k = 0; k < VEC; k++) acc[r][k] = fmaf(val, f[r][k], acc[r][k]);
+#pragma unroll
+    for (int r = 0; r < N; r++) RmwFp16<VEC, 0>::store(a[r], acc[r]);
 }
 
 template <int CUT, bool BULK>
@@ -401,9 +427,11 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
 
     // debugging aid (EFFORT_TRACE): issue / arrival / release times of the first 80 units of pair 0 of CTA 0
     unsigned long long* utrace = (pb.trace && blockIdx.x == 0 && pair == 0) ? pb.trace + (size_t)kNumSMs * 16 : nullptr;
+    if (utrace && tid == 0) utrace[640] = (unsigned long long)clock64();  // time base: the SM's cycle counter
     // pair state.  Both sides count units (seq); unit s uses descriptor slot s % kV4Units, barrier phase (s / kV4Units) & 1.
     // Producer only: ring head, free bytes, oldest unit not yet reclaimed.
     uint32_t seq = 0, tail_seq = 0, head = 0, free_b = kV4RingBytes;
+    uint32_t slot_charged = 0u;  // bulk producers: lane s remembers the ring bytes the unit in descriptor slot s holds
     const uint32_t ticket_saddr = (uint32_t)__cvta_generic_to_shared(&hdr.ticket);
     const uint32_t full0 = (uint32_t)__cvta_generic_to_shared(&hdr.full_bar[pair][0]);
     const uint32_t empty0 = (uint32_t)__cvta_generic_to_shared(&hdr.empty_bar[pair][0]);
@@ -463,8 +491,104 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
             more = __syncthreads_or(m != 0u) != 0;
             V2_TRACE(8);
 
-            if (!consumer) {
-                // ---- 3a. producer of pair `pair`: the next unit nobody has taken goes into the pair's ring ----
+            if (!consumer && BULK) {
+                // ---- 3a. producer of pair `pair`, bulk copies.  Every shared-memory operation of a producer (ticket, record,
+                // barrier test, descriptor) queues behind the consumers' read-modify-writes -- the shared-memory pipe is the
+                // kernel's bottleneck (tools/ubench/stage_cost.cu: ~350 cycles per dependent operation) -- so a producer works
+                // on a WINDOW of units at once, one per lane: one ticket grab (guided: remaining/16, 1..8 units), the records in
+                // parallel, ring space handed out by shuffles, the barrier tests of all outstanding slots in parallel, and each
+                // lane issues its own unit's descriptor + expect_tx + bulk copy. ----
+                const uint32_t nu = hdr.n_units;
+                auto reclaim = [&](bool block) {  // take back the bytes of every unit the consumer has released (in order)
+                    const uint32_t out_n = seq - tail_seq;
+                    const uint32_t rel = ((uint32_t)lane - tail_seq) & (kV4Units - 1);  // slot `lane`: distance from the oldest
+                    const bool mine = lane < kV4Units && rel < out_n;
+                    bool done = false;
+                    if (mine) {
+                        const uint32_t par = ((tail_seq + rel) / kV4Units) & 1u;
+                        done = mbar_test(empty0 + (uint32_t)lane * 8u, par);
+                        if (block && rel == 0 && !done) {
+                            done = mbar_wait_parked(empty0 + (uint32_t)lane * 8u, par);
+                            if (!done && pb.err_flag) atomicExch(pb.err_flag, 3u);
+                            done = true;  // (after the ~1 s bound: give up waiting, the error flag says so)
+                        }
+                    }
+                    const unsigned dm = __ballot_sync(0xffffffffu, done) & 0xFFFFu;
+                    const unsigned rot = ((dm | (dm << 16)) >> (tail_seq & (kV4Units - 1))) & 0xFFFFu;  // bit r: unit tail+r released
+                    const uint32_t n = min((uint32_t)(__ffs((int)~rot) - 1), out_n);
+                    const uint32_t got = __reduce_add_sync(0xffffffffu, (mine && rel < n) ? slot_charged : 0u);
+                    free_b += got;
+                    tail_seq += n;
+                };
+                uint32_t t_seen = 0u, grabs = 0u;
+#pragma unroll 1
+                for (;;) {
+                    const uint32_t left = nu > t_seen ? nu - t_seen : 0u;
+                    // guided grabs, ramped up: the very first units of all pairs must not queue behind a burst
+                    const uint32_t want = min(min((uint32_t)batch.window, 1u + grabs), max(1u, left / (2u * NC)));
+                    grabs++;
+                    uint32_t t0 = 0u;
+                    if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(t0) : "r"(ticket_saddr), "r"(want) : "memory");
+                    t0 = __shfl_sync(0xffffffffu, t0, 0);
+                    if (t0 >= nu) break;
+                    t_seen = t0 + want;
+                    const uint32_t cnt = min(want, nu - t0);
+                    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+                    if ((uint32_t)lane < cnt) rec = ulist[t0 + lane];
+                    const uint32_t my_bytes = rec.y * (uint32_t)seg_bytes;
+                    uint32_t pos = 0u;
+                    if (seq != tail_seq) reclaim(false);
+#pragma unroll 1
+                    while (pos < cnt) {
+                        // ring space for units pos.. in order (warp-uniform arithmetic on broadcast sizes)
+                        uint32_t h = head, f = free_b, n_ok = 0u, my_off = 0u, my_chg = 0u;
+                        const uint32_t slots_free = (uint32_t)kV4Units - (seq - tail_seq);
+                        for (uint32_t l = pos; l < cnt; l++) {
+                            const uint32_t bts = __shfl_sync(0xffffffffu, my_bytes, (int)l);
+                            const uint32_t skip = (h + bts > (uint32_t)kV4RingBytes) ? ((uint32_t)kV4RingBytes - h) : 0u;
+                            if (f < bts + skip || n_ok >= slots_free) break;
+                            const uint32_t off = skip ? 0u : h;
+                            if ((uint32_t)lane == l) { my_off = off; my_chg = bts + skip; }
+                            h = off + bts;
+                            if (h >= (uint32_t)kV4RingBytes) h = 0u;
+                            f -= bts + skip;
+                            n_ok++;
+                        }
+                        if (n_ok == 0u) { reclaim(true); continue; }
+                        const uint32_t k = (uint32_t)lane - pos;  // this lane's unit is the k-th of the batch
+                        if ((uint32_t)lane >= pos && k < n_ok) {
+                            const uint32_t slot = (seq + k) & (kV4Units - 1);
+                            const uint32_t fb = full0 + slot * 8u;
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(desc0 + slot * 16u), "r"(my_off), "r"(rec.y), "r"(rec.z),
+                                         "r"(my_chg) : "memory");
+                            if (utrace && seq + k < 80u) { utrace[8 * (seq + k)] = (unsigned long long)clock64(); utrace[8 * (seq + k) + 3] = (unsigned long long)rec.y; }
+                            mbar_expect_tx(fb, (int)my_bytes);
+                            bulk_g2s(ring_saddr + my_off, bk16 + rec.x, (int)my_bytes, fb, pol);
+                        }
+                        {   // remember what each of the new slots holds (lane s keeps slot s)
+                            const uint32_t rel = ((uint32_t)lane - seq) & (kV4Units - 1);
+                            const uint32_t v = __shfl_sync(0xffffffffu, my_chg, (int)((pos + rel) & 31u));
+                            if (lane < kV4Units && rel < n_ok) slot_charged = v;
+                        }
+                        seq += n_ok;
+                        head = h;
+                        free_b = f;
+                        pos += n_ok;
+                    }
+                }
+                // stop marker for the consumer
+                while (seq - tail_seq >= (uint32_t)kV4Units) reclaim(true);
+                {
+                    const uint32_t slot = seq & (kV4Units - 1);
+                    if (lane == 0) {
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(desc0 + slot * 16u), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+                        mbar_arrive(full0 + slot * 8u);
+                    }
+                    if ((uint32_t)lane == slot) slot_charged = 0u;
+                    seq++;
+                }
+            } else if (!consumer) {
+                // ---- 3a'. producer of pair `pair`, 16-byte cp.async by all lanes, one unit at a time ----
                 const uint32_t nu = hdr.n_units;
                 auto grab = [&]() {
                     uint32_t t = 0u;
@@ -491,26 +615,14 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                     if (lane == 0)
                         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(desc0 + slot * 16u), "r"(off), "r"(len), "r"(valbits),
                                      "r"(bytes + skip) : "memory");
-                    if (utrace && lane == 0 && seq < 80u) { utrace[4 * seq] = gtime_ns(); utrace[4 * seq + 3] = (unsigned long long)len; }
-                    if constexpr (BULK) {
-                        // one bulk copy per unit (slice-major: the run is contiguous); its bytes complete the phase
-                        if (lane == 0) {
-                            if (bytes) {
-                                mbar_expect_tx(fb, (int)bytes);
-                                bulk_g2s(sa, src, (int)bytes, fb, pol);
-                            } else {
-                                mbar_arrive(fb);
-                            }
-                        }
-                    } else {
-                        const uint32_t pieces = len * rs16;
-                        const uint32_t d0 = sa + (uint32_t)lane * 16u;
-                        const uint4* s0p = src + lane;
-                        for (uint32_t q = (uint32_t)lane; q < pieces; q += 32u) cp_async16(d0 + (q - (uint32_t)lane) * 16u, s0p + (q - (uint32_t)lane), pol);
-                        cp_async_arrive_noinc(fb);  // arrives when this lane's copies have landed
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(fb);  // releases the descriptor
-                    }
+                    if (utrace && lane == 0 && seq < 80u) { utrace[8 * seq] = (unsigned long long)clock64(); utrace[8 * seq + 3] = (unsigned long long)len; }
+                    const uint32_t pieces = len * rs16;
+                    const uint32_t d0 = sa + (uint32_t)lane * 16u;
+                    const uint4* s0p = src + lane;
+                    for (uint32_t q = (uint32_t)lane; q < pieces; q += 32u) cp_async16(d0 + (q - (uint32_t)lane) * 16u, s0p + (q - (uint32_t)lane), pol);
+                    cp_async_arrive_noinc(fb);  // arrives when this lane's copies have landed
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(fb);  // releases the descriptor
                     seq++;
                     head = off + bytes;
                     free_b -= bytes + skip;
@@ -527,36 +639,87 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                 }
                 fill(0u, 0u, 0u);  // stop marker for the consumer
             } else {
-                // ---- 3b. consumer ----
+                // ---- 3b. consumer.  Under load every dependent shared-memory operation costs hundreds of cycles (the pipe is
+                // saturated by the read-modify-writes of all eight consumers), so the loop is software pipelined: while a unit
+                // is accumulated the NEXT slot's barrier is tested and its descriptor fetched, and the staged words of the next
+                // four rows (of this unit or, at its end, of the next one) are already on their way. ----
+                bool nx_ok = false, w_ready = false;
+                uint32_t nx_off = 0u, nx_n = 0u, nx_val = 0u;
+                uint32_t w[4][2];
+                auto load4 = [&](uint32_t (&d)[4][2], uint32_t addr) {  // rows past the unit's end are read and ignored
+                    lds64_imm<0>(addr, d[0][0], d[0][1]);
+                    lds64_imm<kRow>(addr, d[1][0], d[1][1]);
+                    lds64_imm<2 * kRow>(addr, d[2][0], d[2][1]);
+                    lds64_imm<3 * kRow>(addr, d[3][0], d[3][1]);
+                };
 #pragma unroll 1
                 for (;;) {
                     const uint32_t slot = seq & (kV4Units - 1);
-                    if (!mbar_wait(full0 + slot * 8u, (seq / kV4Units) & 1u)) {
-                        if (pb.err_flag && lane == 0) atomicExch(pb.err_flag, 2u);
-                        break;
+                    uint32_t hoff, hn, hv;
+                    if (utrace && lane == 0 && seq < 80u) utrace[8 * seq + 1] = (unsigned long long)clock64();
+                    if (nx_ok) {
+                        hoff = nx_off; hn = nx_n; hv = nx_val;
+                    } else {
+                        if (!mbar_wait(full0 + slot * 8u, (seq / kV4Units) & 1u)) {
+                            if (pb.err_flag && lane == 0) atomicExch(pb.err_flag, 2u);
+                            break;
+                        }
+                        uint32_t hs;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hoff), "=r"(hn), "=r"(hv), "=r"(hs) : "r"(desc0 + slot * 16u));
+                        w_ready = false;
                     }
-                    if (utrace && lane == 0 && seq < 80u) utrace[4 * seq + 1] = gtime_ns();
+                    if (utrace && lane == 0 && seq < 80u) utrace[8 * seq + 2] = (unsigned long long)clock64();
                     seq++;
-                    uint32_t hoff, hn, hv, hs;
-                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hoff), "=r"(hn), "=r"(hv), "=r"(hs) : "r"(desc0 + slot * 16u));
                     const int n = (int)hn;
+                    if (utrace && lane == 0 && seq <= 80u && n >= 0) utrace[8 * (seq - 1) + 4] = (unsigned long long)clock64();
                     const uint32_t eb = empty0 + slot * 8u;
                     if (n == 0) {
                         if (lane == 0) mbar_arrive(eb);
                         break;
                     }
+                    nx_ok = false;
+                    if (batch.lookahead) {  // look ahead: has the next unit landed already?  (the producers run several units ahead)
+                        const uint32_t nslot = seq & (kV4Units - 1);
+                        nx_ok = mbar_test(full0 + nslot * 8u, (seq / kV4Units) & 1u);
+                        if (nx_ok) {
+                            uint32_t hs;
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(nx_off), "=r"(nx_n), "=r"(nx_val), "=r"(hs) : "r"(desc0 + nslot * 16u));
+                        }
+                    }
                     const float val = __uint_as_float(hv);
                     const uint32_t sa = ring_saddr + hoff;
-                    if (full_width) {
+                    if (full_width && !batch.lookahead) {
                         uint32_t a0 = sa + (uint32_t)(lane * LB);
                         int r = 0;
-                        for (; r + 4 <= n; r += 4, a0 += 4 * kRow) accumulate_unit_fp16<VEC, 4, kRow>(base_lane, val, a0);
+                        for (; r + 4 <= n; r += 4, a0 += 4 * kRow) {
+                            accumulate_unit_fp16<VEC, 4, kRow>(base_lane, val, a0);
+                            if (utrace && lane == 0 && seq <= 80u && r == 0) utrace[8 * (seq - 1) + 5] = (unsigned long long)clock64();
+                        }
                         switch (n - r) {
                             case 1: accumulate_unit_fp16<VEC, 1, kRow>(base_lane, val, a0); break;
                             case 2: accumulate_unit_fp16<VEC, 2, kRow>(base_lane, val, a0); break;
                             case 3: accumulate_unit_fp16<VEC, 3, kRow>(base_lane, val, a0); break;
                             default: break;
                         }
+                    } else if (full_width) {
+                        uint32_t a0 = sa + (uint32_t)(lane * LB);
+                        if (!w_ready) load4(w, a0);
+                        for (int r = 0; r < n; r += 4) {
+                            const bool last = r + 4 >= n;
+                            uint32_t wn[4][2];
+                            if (!last) load4(wn, a0 + 4 * kRow);
+                            else if (nx_ok) load4(wn, ring_saddr + nx_off + (uint32_t)(lane * LB));
+                            switch (min(4, n - r)) {
+                                case 1: accumulate_rows_fp16<VEC, 1>(base_lane, val, w); break;
+                                case 2: accumulate_rows_fp16<VEC, 2>(base_lane, val, w); break;
+                                case 3: accumulate_rows_fp16<VEC, 3>(base_lane, val, w); break;
+                                default: accumulate_rows_fp16<VEC, 4>(base_lane, val, w); break;
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; q++) { w[q][0] = wn[q][0]; w[q][1] = wn[q][1]; }
+                            a0 += 4 * kRow;
+                        }
+                        w_ready = nx_ok;
                     } else {  // narrow slice: rows are seg_bytes apart, R rows per step, lanes past the slice idle
                         for (int st = 0; st * R < n; st++) {
                             const int r = st * R + rowslot;
@@ -566,9 +729,10 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                             accumulate_words<SLOTS, VEC>(base_lane, ok ? val : 0.f, ww);
                         }
                     }
+                    if (utrace && lane == 0 && seq <= 80u) utrace[8 * (seq - 1) + 6] = (unsigned long long)clock64();
                     __syncwarp();  // every lane has read the unit's bytes
                     if (lane == 0) mbar_arrive(eb);
-                    if (utrace && lane == 0 && seq <= 80u) utrace[4 * (seq - 1) + 2] = gtime_ns();
+                    if (utrace && lane == 0 && seq <= 80u) utrace[8 * (seq - 1) + 7] = (unsigned long long)clock64();
                 }
             }
         } while (more);

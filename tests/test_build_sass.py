@@ -47,3 +47,34 @@ def test_fused_kernel_instruction_selection(lib):
     assert "BAR.SYNC.DEFER_BLOCKING 0x1, 0x80" in sass              # the four-warp named barrier of the cutoff
     assert not re.search(r"\b(HMMA|IMMA|UTCHMMA|UTCQMMA|QGMMA|HGMMA)\b", sass)   # no tensor cores on this path
     assert "STL" not in sass and "LDL" not in sass
+
+
+def _fn(lib, pattern):
+    names = [l.split()[-1].rstrip(":") for l in _run(["--dump-resource-usage"]).splitlines() if l.strip().startswith("Function")]
+    hit = [n for n in names if pattern in n]
+    assert len(hit) == 1, (pattern, hit)
+    return hit[0]
+
+
+def test_default_kernel_streams_with_async_copies(lib):
+    """bucket_mul_v4_kernel<select, cp.async> -- the default path of round 2: weights reach shared memory through LDGSTS
+    (16-byte cp.async), completion through ARRIVES.LDGSTSBAR on an mbarrier, the consumer warps wait with
+    SYNCS.PHASECHK, results leave as 16-byte vector reductions; no spills, no tensor-core instructions."""
+    usage = _run(["--dump-resource-usage"])
+    recs = re.findall(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", usage)
+    v4 = [r for r in recs if "bucket_mul_v4_kernel" in r[0]]
+    assert len(v4) == 4            # select / bisect x cp.async / bulk
+    for name, reg, stack, _, local in v4:
+        assert int(stack) == 0 and int(local) == 0 and int(reg) <= 128, (name, reg, stack, local)
+    sass = _run(["-sass", "-fun", _fn(lib, "bucket_mul_v4_kernelILi0ELb0")])
+    assert "LDGSTS.E.BYPASS.128" in sass and "ARRIVES.LDGSTSBAR" in sass
+    assert "SYNCS.PHASECHK.TRANS64.TRYWAIT" in sass and "SYNCS.ARRIVE.TRANS64" in sass
+    assert "REDG.E.ADD.F32x4" in sass
+    assert "HSET2.BF16_V2" in sass and "HADD2.BF16_V2" in sass      # the exact select counts two products per op
+    assert not re.search(r"\b(HMMA|IMMA|UTCHMMA|UTCQMMA|QGMMA|HGMMA)\b", sass)
+    assert "STL" not in sass and "LDL" not in sass
+
+
+def test_bulk_variant_uses_tma_bulk_copies(lib):
+    sass = _run(["-sass", "-fun", _fn(lib, "bucket_mul_v4_kernelILi0ELb1")])
+    assert "UBLKCP.S.G" in sass and "LDGSTS" not in sass

@@ -41,12 +41,14 @@ for rep in range(3):
     for k, nm in names.items():
         rel = (t[:, k] - t0) / 1000.0
         print(f"   {nm:10s} min {rel.min():7.2f}  median {np.median(rel):7.2f}  max {rel.max():7.2f} us")
-    ub = np.zeros((80, 4), dtype=np.uint64)
+    ub = np.zeros(648, dtype=np.uint64)
     if L.effort_debug_read_unit_trace(ctx._h, ub.ctypes.data) == 0 and rep == 2:
-        u = ub.astype(np.int64)
-        print("   units of pair 0, CTA 0 (us from the CTA's start): rows, copies issued, data seen by the consumer, released")
+        base = int(ub[640])
+        u = ub[:640].reshape(80, 8).astype(np.int64)
+        print("   units of pair 0, CTA 0 -- SM cycles since the CTA started: rows | producer issued | consumer: starts waiting, "
+              "barrier passed, descriptor read, first 4 rows done, all rows done, slot released")
         for k in range(80):
             if u[k, 0] == 0:
                 break
-            print(f"     unit {k:2d}: {int(u[k,3]):2d} rows  issued {(u[k,0]-t[0,0])/1000.0:6.2f}  arrived {(u[k,1]-t[0,0])/1000.0:6.2f}  "
-                  f"released {(u[k,2]-t[0,0])/1000.0:6.2f}")
+            c = [int(u[k, j]) - base if u[k, j] else -1 for j in (0, 1, 2, 4, 5, 6, 7)]
+            print(f"     unit {k:2d}: {int(u[k,3]):2d} rows | {c[0]:6d} | {c[1]:6d} {c[2]:6d} {c[3]:6d} {c[4]:6d} {c[5]:6d} {c[6]:6d}")
