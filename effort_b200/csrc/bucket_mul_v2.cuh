@@ -77,8 +77,8 @@ struct V2Batch {
     int dynamic;             // 1: warps take units from a shared counter; 0: static round robin
     int ring_bytes;          // bucket_mul_v3_kernel: bytes of the producer's staging ring
     int prefetch;            // bucket_mul_v4_kernel: speculative L2 prefetch of the rows the hint selects
+    int lookahead;           // bucket_mul_v4_kernel: consumers test the next unit's barrier / fetch its descriptor early
     int window;              // bucket_mul_v4_kernel (bulk): most units a producer takes per ticket grab (1..8)
-    int lookahead;           // bucket_mul_v4_kernel: 1 = consumers fetch the next unit's descriptor / rows early
     int cta_begin[kMulBatchMax + 1];
     V2Problem p[kMulBatchMax];
 };

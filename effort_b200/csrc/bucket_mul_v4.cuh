@@ -146,23 +146,6 @@ __device__ __forceinline__ float select_cutoff_group(const uint32_t (&keys)[16],
     return __uint_as_float((uint32_t)(L + 1) << 16);
 }
 
-// the read-modify-writes of N rows whose staged words are already in registers (cf. accumulate_unit_fp16)
-template <int VEC, int N>
-__device__ __forceinline__ void accumulate_rows_fp16(uint32_t base_lane, float val, const uint32_t (&w)[4][2]) {
-    uint32_t a[N][VEC];
-    float f[N][VEC], acc[N][VEC];
-#pragma unroll
-    for (int r = 0; r < N; r++) AccFp16<VEC, 0>::addr(w[r], base_lane, a[r], f[r]);
-#pragma unroll
-    for (int r = 0; r < N; r++) RmwFp16<VEC, 0>::load(a[r], acc[r]);
-#pragma unroll
-    for (int r = 0; r < N; r++)
-#pragma unroll
-        for (int k = 0; k < VEC; k++) acc[r][k] = fmaf(val, f[r][k], acc[r][k]);
-#pragma unroll
-    for (int r = 0; r < N; r++) RmwFp16<VEC, 0>::store(a[r], acc[r]);
-}
-
 template <int CUT, bool BULK>
 __global__ void __launch_bounds__(kV2Threads, 1)
 bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
@@ -639,23 +622,14 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                 }
                 fill(0u, 0u, 0u);  // stop marker for the consumer
             } else {
-                // ---- 3b. consumer.  Under load every dependent shared-memory operation costs hundreds of cycles (the pipe is
-                // saturated by the read-modify-writes of all eight consumers), so the loop is software pipelined: while a unit
-                // is accumulated the NEXT slot's barrier is tested and its descriptor fetched, and the staged words of the next
-                // four rows (of this unit or, at its end, of the next one) are already on their way. ----
-                bool nx_ok = false, w_ready = false;
+                // ---- 3b. consumer: wait for the next unit of the pair's ring, read its rows, run the read-modify-writes ----
+                unsigned long long rows_done = 0ull;
+                bool nx_ok = false;  // the next unit had already landed when the current one was started: its descriptor is in nx_*
                 uint32_t nx_off = 0u, nx_n = 0u, nx_val = 0u;
-                uint32_t w[4][2];
-                auto load4 = [&](uint32_t (&d)[4][2], uint32_t addr) {  // rows past the unit's end are read and ignored
-                    lds64_imm<0>(addr, d[0][0], d[0][1]);
-                    lds64_imm<kRow>(addr, d[1][0], d[1][1]);
-                    lds64_imm<2 * kRow>(addr, d[2][0], d[2][1]);
-                    lds64_imm<3 * kRow>(addr, d[3][0], d[3][1]);
-                };
 #pragma unroll 1
                 for (;;) {
                     const uint32_t slot = seq & (kV4Units - 1);
-                    uint32_t hoff, hn, hv;
+                    uint32_t hoff, hn, hv, hs;
                     if (utrace && lane == 0 && seq < 80u) utrace[8 * seq + 1] = (unsigned long long)clock64();
                     if (nx_ok) {
                         hoff = nx_off; hn = nx_n; hv = nx_val;
@@ -664,12 +638,17 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                             if (pb.err_flag && lane == 0) atomicExch(pb.err_flag, 2u);
                             break;
                         }
-                        uint32_t hs;
                         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hoff), "=r"(hn), "=r"(hv), "=r"(hs) : "r"(desc0 + slot * 16u));
-                        w_ready = false;
                     }
                     if (utrace && lane == 0 && seq < 80u) utrace[8 * seq + 2] = (unsigned long long)clock64();
                     seq++;
+                    nx_ok = false;
+                    if (batch.lookahead && hn != 0u) {  // both round trips of the NEXT unit's hand-over overlap this unit's rows
+                        const uint32_t nslot = seq & (kV4Units - 1);
+                        nx_ok = mbar_test(full0 + nslot * 8u, (seq / kV4Units) & 1u);
+                        if (nx_ok)
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(nx_off), "=r"(nx_n), "=r"(nx_val), "=r"(hs) : "r"(desc0 + nslot * 16u));
+                    }
                     const int n = (int)hn;
                     if (utrace && lane == 0 && seq <= 80u && n >= 0) utrace[8 * (seq - 1) + 4] = (unsigned long long)clock64();
                     const uint32_t eb = empty0 + slot * 8u;
@@ -677,18 +656,10 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                         if (lane == 0) mbar_arrive(eb);
                         break;
                     }
-                    nx_ok = false;
-                    if (batch.lookahead) {  // look ahead: has the next unit landed already?  (the producers run several units ahead)
-                        const uint32_t nslot = seq & (kV4Units - 1);
-                        nx_ok = mbar_test(full0 + nslot * 8u, (seq / kV4Units) & 1u);
-                        if (nx_ok) {
-                            uint32_t hs;
-                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(nx_off), "=r"(nx_n), "=r"(nx_val), "=r"(hs) : "r"(desc0 + nslot * 16u));
-                        }
-                    }
+                    rows_done += (unsigned long long)n;
                     const float val = __uint_as_float(hv);
                     const uint32_t sa = ring_saddr + hoff;
-                    if (full_width && !batch.lookahead) {
+                    if (full_width) {
                         uint32_t a0 = sa + (uint32_t)(lane * LB);
                         int r = 0;
                         for (; r + 4 <= n; r += 4, a0 += 4 * kRow) {
@@ -701,25 +672,6 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                             case 3: accumulate_unit_fp16<VEC, 3, kRow>(base_lane, val, a0); break;
                             default: break;
                         }
-                    } else if (full_width) {
-                        uint32_t a0 = sa + (uint32_t)(lane * LB);
-                        if (!w_ready) load4(w, a0);
-                        for (int r = 0; r < n; r += 4) {
-                            const bool last = r + 4 >= n;
-                            uint32_t wn[4][2];
-                            if (!last) load4(wn, a0 + 4 * kRow);
-                            else if (nx_ok) load4(wn, ring_saddr + nx_off + (uint32_t)(lane * LB));
-                            switch (min(4, n - r)) {
-                                case 1: accumulate_rows_fp16<VEC, 1>(base_lane, val, w); break;
-                                case 2: accumulate_rows_fp16<VEC, 2>(base_lane, val, w); break;
-                                case 3: accumulate_rows_fp16<VEC, 3>(base_lane, val, w); break;
-                                default: accumulate_rows_fp16<VEC, 4>(base_lane, val, w); break;
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; q++) { w[q][0] = wn[q][0]; w[q][1] = wn[q][1]; }
-                            a0 += 4 * kRow;
-                        }
-                        w_ready = nx_ok;
                     } else {  // narrow slice: rows are seg_bytes apart, R rows per step, lanes past the slice idle
                         for (int st = 0; st * R < n; st++) {
                             const int r = st * R + rowslot;
@@ -733,6 +685,12 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                     __syncwarp();  // every lane has read the unit's bytes
                     if (lane == 0) mbar_arrive(eb);
                     if (utrace && lane == 0 && seq <= 80u) utrace[8 * (seq - 1) + 7] = (unsigned long long)clock64();
+                }
+                if (pb.trace && blockIdx.x == 0 && lane == 0) {  // when every consumer of CTA 0 ran dry, and how much it did
+                    unsigned long long* fin = pb.trace + (size_t)kNumSMs * 16 + 648;
+                    fin[warp] = (unsigned long long)clock64();
+                    fin[16 + warp] = rows_done;
+                    fin[32 + warp] = (unsigned long long)seq;
                 }
             }
         } while (more);

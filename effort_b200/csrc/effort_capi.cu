@@ -86,11 +86,12 @@ struct effort_ctx {
     unsigned* v2_sync = nullptr;          // [kMaxBatch][kV2MaxSlices][2] arrive/depart counters (overwrite protocol)
     unsigned* v2_err = nullptr;           // [1] set by a kernel whose overwrite barrier timed out
     int cutoff_mode = 0;                  // EFFORT_CUTOFF_SELECT / EFFORT_CUTOFF_BISECT
-    int stage_mode = 3;                   // 3 = consumer/producer warp pairs, whole-input units (slice-major FP16 weights; default)
+    int stage_mode = 4;                   // 4 = consumer/producer warp pairs fed by bulk copies (slice-major FP16 weights; default), 3 = the pairs with 16-byte cp.async
                                           // 2 = one TMA producer warp + byte ring (slice-major FP16 weights; measured slower)
                                           // 0 = per-warp cp.async rings, units of <= 4 rows (any layout, Q4)
     int engine = 2;                       // 2 = bucket_mul_v2_kernel, 1 = round-1 fused kernel + integrate
-    int window = 8, lookahead = 0;        // bucket_mul_v4 experiments (see V2Batch)
+    int lookahead = 1;                    // bucket_mul_v4 consumers: test the next slot and fetch its descriptor while the current unit is accumulated
+    int window = 8;                       // bucket_mul_v4 bulk producers: most units per ticket grab
     int prefetch = 0;                     // bucket_mul_v4: speculative L2 prefetch of the rows the previous cutoff selects
                                           // (measured: no gain at effort 0.25, -13 % at 1.0: the gather is not DRAM-latency bound)
     int use_hint = 1;                     // bucket_mul_v4: the select starts from the matrix's previous cutoff
@@ -155,16 +156,16 @@ extern "C" int effort_ctx_create(int device, effort_ctx_t** ctx_out) {
     CK(cudaMemset(c->sel_counts, 0, sizeof(uint32_t) * kMaxBatch * c->n_sms));
     c->sel_cap = (size_t)kMaxBatch * c->n_sms;
     { const char* e = getenv("EFFORT_CUTOFF"); if (e && !strcmp(e, "bisect")) c->cutoff_mode = 1; }
-    { const char* e = getenv("EFFORT_STAGE"); if (e) c->stage_mode = !strcmp(e, "ldgsts") ? 0 : !strcmp(e, "tma") ? 2 : !strcmp(e, "bulk") ? 4 : 3; }
+    { const char* e = getenv("EFFORT_STAGE"); if (e) c->stage_mode = !strcmp(e, "ldgsts") ? 0 : !strcmp(e, "tma") ? 2 : !strcmp(e, "pairs-ldgsts") ? 3 : 4; }
     { const char* e = getenv("EFFORT_ENGINE"); if (e && atoi(e) == 1) c->engine = 1; }
     { const char* e = getenv("EFFORT_DYN"); if (e) c->dynamic = atoi(e) ? 1 : 0; }
     { const char* e = getenv("EFFORT_PREFETCH"); if (e) c->prefetch = atoi(e) ? 1 : 0; }
-    { const char* e = getenv("EFFORT_WINDOW"); if (e && atoi(e) >= 1 && atoi(e) <= 8) c->window = atoi(e); }
     { const char* e = getenv("EFFORT_LOOKAHEAD"); if (e) c->lookahead = atoi(e) ? 1 : 0; }
+    { const char* e = getenv("EFFORT_WINDOW"); if (e && atoi(e) >= 1 && atoi(e) <= 8) c->window = atoi(e); }
     { const char* e = getenv("EFFORT_HINT"); if (e) c->use_hint = atoi(e) ? 1 : 0; }
     if (getenv("EFFORT_TRACE")) {
-        CK(cudaMalloc(&c->trace, sizeof(unsigned long long) * (16 * c->n_sms + 648)));
-        CK(cudaMemset(c->trace, 0, sizeof(unsigned long long) * (16 * c->n_sms + 648)));
+        CK(cudaMalloc(&c->trace, sizeof(unsigned long long) * (16 * c->n_sms + 648 + 48)));
+        CK(cudaMemset(c->trace, 0, sizeof(unsigned long long) * (16 * c->n_sms + 648 + 48)));
     }
     *ctx_out = c;
     return EFFORT_OK;
@@ -181,8 +182,8 @@ extern "C" int effort_ctx_set_option(effort_ctx_t* c, const char* name, int valu
     if (!strcmp(name, "engine")) { if (value != 1 && value != 2) return EFFORT_EINVAL; c->engine = value; return EFFORT_OK; }
     if (!strcmp(name, "stage")) { if (value != 0 && value != 2 && value != 3 && value != 4) return EFFORT_EINVAL; c->stage_mode = value; return EFFORT_OK; }
     if (!strcmp(name, "hint")) { if (value != 0 && value != 1) return EFFORT_EINVAL; c->use_hint = value; return EFFORT_OK; }
-    if (!strcmp(name, "window")) { if (value < 1 || value > 8) return EFFORT_EINVAL; c->window = value; return EFFORT_OK; }
     if (!strcmp(name, "lookahead")) { if (value != 0 && value != 1) return EFFORT_EINVAL; c->lookahead = value; return EFFORT_OK; }
+    if (!strcmp(name, "window")) { if (value < 1 || value > 8) return EFFORT_EINVAL; c->window = value; return EFFORT_OK; }
     if (!strcmp(name, "prefetch")) { if (value != 0 && value != 1) return EFFORT_EINVAL; c->prefetch = value; return EFFORT_OK; }
     if (!strcmp(name, "dynamic")) { if (value != 0 && value != 1) return EFFORT_EINVAL; c->dynamic = value; return EFFORT_OK; }
     return EFFORT_EINVAL;
@@ -200,8 +201,8 @@ extern "C" int effort_ctx_error_flag(effort_ctx_t* c, unsigned* flag_out, void* 
 extern "C" int effort_debug_read_unit_trace(effort_ctx_t* c, unsigned long long* host648) {
     if (!c || !c->trace || !host648) return EFFORT_EINVAL;
     CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(host648, c->trace + 16 * c->n_sms, sizeof(unsigned long long) * 648, cudaMemcpyDeviceToHost));
-    CK(cudaMemset(c->trace + 16 * c->n_sms, 0, sizeof(unsigned long long) * 648));
+    CK(cudaMemcpy(host648, c->trace + 16 * c->n_sms, sizeof(unsigned long long) * (648 + 48), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(c->trace + 16 * c->n_sms, 0, sizeof(unsigned long long) * (648 + 48)));
     return EFFORT_OK;
 }
 

@@ -86,17 +86,20 @@ int effort_ctx_set_cutoff_mode(effort_ctx_t* ctx, int mode);
 /* Tuning / A-B knobs of the fused operator (tests and tools; every value computes the same operator):
  *   "engine"   2 (default) round-2 kernel: one launch per group, staged streaming, reductions into `out`;
  *              1 round-1 kernel + integrate launch (deterministic fp32 order)
- *   "stage"    3 (default) eight consumer warps accumulate, eight producer warps stage whole-input units (1..16 rows)
- *              with cp.async into per-pair rings and hand them over through mbarriers (slice-major FP16 weights; other
- *              weights take stage 0); 4 the same pairs with one bulk copy (cp.async.bulk) per unit; 2 one TMA (cp.async.bulk) producer warp, a shared byte ring and 16 consumers
- *              (slice-major FP16 weights; measured slower: the single producer's serial issue is the limit);
- *              0 sixteen self-serving warps with private cp.async rings, units of at most 4 rows
+ *   "stage"    4 (default) eight consumer warps accumulate, eight producer warps stage whole-input units (1..16 rows)
+ *              with bulk async copies (cp.async.bulk, several units per producer step) into per-pair rings and hand them over
+ *              through mbarriers (slice-major FP16 weights; other weights take stage 0); 3 the same pairs fed by 16-byte
+ *              cp.async, one unit per producer step; 2 one TMA producer warp, a shared byte ring and 16 consumers (measured
+ *              slower: the single producer's serial issue is the limit); 0 sixteen self-serving warps with private cp.async
+ *              rings, units of at most 4 rows
+ *   "window"   1..8 (default 8) stage 4: most units a producer takes per ticket grab
+ *   "lookahead" 1 (default) / 0 stages 3-4: consumers test the next slot's barrier and fetch its descriptor early
  *   "dynamic"  per-warp rings (stage 0/1) only: 0 (default) static round robin of the units, 1 units from a shared counter
  *   "hint"     1 (default) stage 3 only: the exact select starts its search at the cutoff the same matrix produced on the
  *              previous call (3 rounds instead of 8 when it moved by less than 12 %; the result never depends on it)
  *   "prefetch" 0 (default) / 1 stage 3 only: while the cutoff is being computed, rows that the matrix's previous cutoff
  *              would select are prefetched into L2 (measured: no gain -- the gather is not DRAM-latency bound)
- * Returns EFFORT_EINVAL for an unknown name or value.  Environment defaults: EFFORT_ENGINE, EFFORT_STAGE (ldgsts|tma|bulk),
+ * Returns EFFORT_EINVAL for an unknown name or value.  Environment defaults: EFFORT_ENGINE, EFFORT_STAGE (ldgsts|tma|pairs-ldgsts), EFFORT_WINDOW, EFFORT_LOOKAHEAD,
  * EFFORT_DYN, EFFORT_PREFETCH, EFFORT_HINT. */
 int effort_ctx_set_option(effort_ctx_t* ctx, const char* name, int value);
 /* Non-zero once a fused kernel of this context gave up waiting for a co-resident CTA (2 s): its output is invalid.

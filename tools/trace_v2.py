@@ -41,10 +41,13 @@ for rep in range(3):
     for k, nm in names.items():
         rel = (t[:, k] - t0) / 1000.0
         print(f"   {nm:10s} min {rel.min():7.2f}  median {np.median(rel):7.2f}  max {rel.max():7.2f} us")
-    ub = np.zeros(648, dtype=np.uint64)
+    ub = np.zeros(648 + 48, dtype=np.uint64)
     if L.effort_debug_read_unit_trace(ctx._h, ub.ctypes.data) == 0 and rep == 2:
         base = int(ub[640])
         u = ub[:640].reshape(80, 8).astype(np.int64)
+        fin = ub[648:].astype(np.int64)
+        print("   consumers of CTA 0: ran dry at cycle / rows / units:",
+              "  ".join(f"{int(fin[w]) - base if fin[w] else -1}/{int(fin[16 + w])}/{int(fin[32 + w])}" for w in range(8)))
         print("   units of pair 0, CTA 0 -- SM cycles since the CTA started: rows | producer issued | consumer: starts waiting, "
               "barrier passed, descriptor read, first 4 rows done, all rows done, slot released")
         for k in range(80):
