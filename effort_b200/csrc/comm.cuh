@@ -37,18 +37,31 @@ struct P2PLayout {  // offsets inside a rank's symmetric buffer
 struct P2PArgs {
     unsigned char* peer[kP2PMaxRanks];  // every rank's symmetric buffer (peer[rank] = own)
     int rank, world, site;
+    unsigned* err;  // the context's error flag: a wait that gives up (peer died / never launched) writes 4 here
 };
 
 __device__ __forceinline__ void ll_store(unsigned long long* p, float v, unsigned seq) {
     const unsigned long long pkt = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(v);
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(pkt) : "memory");
 }
-__device__ __forceinline__ float ll_wait(const unsigned long long* p, unsigned seq) {
+// bounded: a peer that never sends (crashed process, mismatched launch order) must not hang this GPU.  After ~2 s the
+// wait gives up, raises the context's error flag (read with effort_ctx_error_flag: 4) and returns 0.
+__device__ __forceinline__ float ll_wait(const unsigned long long* p, unsigned seq, unsigned* err) {
     unsigned long long pkt;
-    do {
-        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(pkt) : "l"(p) : "memory");
-    } while ((unsigned)(pkt >> 32) != seq);
-    return __uint_as_float((unsigned)pkt);
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(pkt) : "l"(p) : "memory");
+    if ((unsigned)(pkt >> 32) == seq) return __uint_as_float((unsigned)pkt);
+    const unsigned long long t0 = gtime_ns();
+    for (;;) {
+#pragma unroll 1
+        for (int k = 0; k < 256; k++) {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(pkt) : "l"(p) : "memory");
+            if ((unsigned)(pkt >> 32) == seq) return __uint_as_float((unsigned)pkt);
+        }
+        if (gtime_ns() - t0 > 2000000000ull) {
+            if (err) atomicExch(err, 4u);
+            return 0.f;
+        }
+    }
 }
 __device__ __forceinline__ unsigned long long* ll_slot(const P2PArgs& a, int peer, int src_rank, int count) {
     return reinterpret_cast<unsigned long long*>(a.peer[peer] + P2PLayout::data_off + (size_t)a.site * kP2PSiteBytes) +
@@ -74,9 +87,9 @@ p2p_collective_kernel(const P2PArgs a, const float* __restrict__ send, float* __
         float s = 0.f;
         for (int r = 0; r < a.world; r++) {
             if (MODE == 0) {
-                if (r != a.rank) out[(size_t)r * count + i] = ll_wait(ll_slot(a, a.rank, r, count) + i, seq);
+                if (r != a.rank) out[(size_t)r * count + i] = ll_wait(ll_slot(a, a.rank, r, count) + i, seq, a.err);
             } else {
-                s += (r == a.rank) ? send[i] : ll_wait(ll_slot(a, a.rank, r, count) + i, seq);
+                s += (r == a.rank) ? send[i] : ll_wait(ll_slot(a, a.rank, r, count) + i, seq, a.err);
             }
         }
         if (MODE == 1) out[i] = s;
@@ -115,7 +128,7 @@ p2p_allreduce_residual_rmsnorm_kernel(const P2PArgs a, const float* __restrict__
         x[k] = 0.f;
         if (i < dim) {
             float s = 0.f;
-            for (int r = 0; r < a.world; r++) s += (r == a.rank) ? mine[k] : ll_wait(ll_slot(a, a.rank, r, dim) + i, seq);
+            for (int r = 0; r < a.world; r++) s += (r == a.rank) ? mine[k] : ll_wait(ll_slot(a, a.rank, r, dim) + i, seq, a.err);
             x[k] = h[i] + s;
             h[i] = x[k];
             ss += x[k] * x[k];
@@ -157,7 +170,7 @@ p2p_silu_allgather_kernel(const P2PArgs a, const float* __restrict__ x1, const f
     for (int r = 0; r < a.world; r++) {
         if (r == a.rank) continue;
         for (int i = threadIdx.x; i < n_local; i += blockDim.x)
-            x2_full[(size_t)r * n_local + i] = ll_wait(ll_slot(a, a.rank, r, n_local) + i, seq);
+            x2_full[(size_t)r * n_local + i] = ll_wait(ll_slot(a, a.rank, r, n_local) + i, seq, a.err);
     }
     __syncthreads();
     if (threadIdx.x == 0) *seq_ptr = seq;

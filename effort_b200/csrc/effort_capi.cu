@@ -1119,7 +1119,7 @@ static int p2p_launch(effort_ctx* ctx, int site, const float* send, float* out, 
         return EFFORT_ESHAPE;
     P2PArgs a{};
     for (int p = 0; p < ctx->comm_world; p++) a.peer[p] = (unsigned char*)ctx->p2p_peer[p];
-    a.rank = ctx->comm_rank; a.world = ctx->comm_world; a.site = site;
+    a.rank = ctx->comm_rank; a.world = ctx->comm_world; a.site = site; a.err = ctx->v2_err;
     CK(launch_pdl(p2p_collective_kernel<MODE>, dim3(kP2PBlocks), dim3(kP2PThreads), 0, s, a, send, out, (int)count));
     LAUNCHED();
     return EFFORT_OK;
@@ -1221,6 +1221,9 @@ static int model_alloc(effort_model* m, T*& p, size_t n) {
     return EFFORT_OK;
 }
 
+static int model_create_buffers(effort_model* m, effort_ctx* ctx, const effort_model_config_t* cfg, int G);
+extern "C" int effort_model_destroy(effort_model_t* m);
+
 extern "C" int effort_model_create(effort_ctx_t* ctx, const effort_model_config_t* cfg, effort_model_t** m_out) {
     if (!ctx || !cfg || !m_out) return EFFORT_EINVAL;
     *m_out = nullptr;
@@ -1237,6 +1240,16 @@ extern "C" int effort_model_create(effort_ctx_t* ctx, const effort_model_config_
     m->ctx = ctx; m->cfg = *cfg;
     m->layers.resize(cfg->n_layers);
     m->cfg.tp_size = G;
+    const int rc_alloc = model_create_buffers(m, ctx, cfg, G);
+    if (rc_alloc) {  // every failure path releases what was allocated so far
+        effort_model_destroy(m);
+        return rc_alloc;
+    }
+    *m_out = m;
+    return EFFORT_OK;
+}
+
+static int model_create_buffers(effort_model* m, effort_ctx* ctx, const effort_model_config_t* cfg, int G) {
     const size_t kv = (size_t)cfg->max_seq * (cfg->n_kv_heads / G) * cfg->head_dim;
     int rc = 0;
     for (auto& l : m->layers) {
@@ -1271,7 +1284,6 @@ extern "C" int effort_model_create(effort_ctx_t* ctx, const effort_model_config_
     CK(cudaMallocHost(&m->h_token, sizeof(int)));
     CK(cudaMallocHost(&m->h_next, sizeof(int)));
     CK(cudaMallocHost(&m->h_logits, sizeof(float) * cfg->vocab));
-    *m_out = m;
     return EFFORT_OK;
 }
 
@@ -1531,7 +1543,7 @@ static int model_enqueue_token(effort_model* m, double effort, cudaStream_t s) {
     auto p2p_args = [&](int site) {
         P2PArgs a{};
         for (int p = 0; p < G; p++) a.peer[p] = (unsigned char*)ctx->p2p_peer[p];
-        a.rank = ctx->comm_rank; a.world = G; a.site = site;
+        a.rank = ctx->comm_rank; a.world = G; a.site = site; a.err = ctx->v2_err;
         return a;
     };
     for (int li = 0; li < c.n_layers; li++) {

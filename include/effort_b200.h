@@ -95,14 +95,16 @@ int effort_ctx_set_cutoff_mode(effort_ctx_t* ctx, int mode);
  *   "window"   1..8 (default 8) stage 4: most units a producer takes per ticket grab
  *   "lookahead" 1 (default) / 0 stages 3-4: consumers test the next slot's barrier and fetch its descriptor early
  *   "dynamic"  per-warp rings (stage 0/1) only: 0 (default) static round robin of the units, 1 units from a shared counter
- *   "hint"     1 (default) stage 3 only: the exact select starts its search at the cutoff the same matrix produced on the
+ *   "hint"     1 (default) stages 3-4: the exact select starts its search at the cutoff the same matrix produced on the
  *              previous call (3 rounds instead of 8 when it moved by less than 12 %; the result never depends on it)
- *   "prefetch" 0 (default) / 1 stage 3 only: while the cutoff is being computed, rows that the matrix's previous cutoff
+ *   "prefetch" 0 (default) / 1 stages 3-4: while the cutoff is being computed, rows that the matrix's previous cutoff
  *              would select are prefetched into L2 (measured: no gain -- the gather is not DRAM-latency bound)
  * Returns EFFORT_EINVAL for an unknown name or value.  Environment defaults: EFFORT_ENGINE, EFFORT_STAGE (ldgsts|tma|pairs-ldgsts), EFFORT_WINDOW, EFFORT_LOOKAHEAD,
  * EFFORT_DYN, EFFORT_PREFETCH, EFFORT_HINT. */
 int effort_ctx_set_option(effort_ctx_t* ctx, const char* name, int value);
-/* Non-zero once a fused kernel of this context gave up waiting for a co-resident CTA (2 s): its output is invalid.
+/* Non-zero once a kernel of this context gave up a bounded wait: its output is invalid.  1 = the overwrite protocol
+ * of a fused GEMV (co-resident CTAs never arrived), 2 / 3 = a consumer / producer warp of bucket_mul_v4 waited ~1 s on
+ * its ring, 4 = a tensor-parallel exchange waited 2 s for a peer's packets (peer died or launched in another order).
  * Synchronises `stream`. */
 int effort_ctx_error_flag(effort_ctx_t* ctx, unsigned* flag_out, void* stream);
 
