@@ -338,32 +338,46 @@ def run_ours(args, rank, local_rank, world):
                 extras[str(eff)] = max(8, args.steps // 4) / (ms_e / 1e3)
         extras[str(args.effort)] = tok_s / streams_total
 
-        # tensor parallel: the sharded model must compute what the unsharded one does (rank 0 holds both)
+        # tensor parallel: the sharded model must compute what the unsharded one does (rank 0 holds both).  Asserted at
+        # effort 1.0, where only the fp32 summation order differs; the bench effort is recorded next to it without a bar:
+        # on a random-init network a low-effort selection is knife-edge and ANY reordering compounds through 32 layers
+        # ("Depth and chaos") -- the 2-layer comparison with a bar lives in tests/test_gpu_tp.py.
         tp_check = None
         if tp and not args.quick:
             ref_model = DecodeModel.random_init(cfg, seed=1234) if rank == 0 else None
-            model.reset()
-            cs_tp = []
-            tok = torch.tensor([1], dtype=torch.int32, device="cuda")
-            if rank == 0:
-                ref_model.reset()
-            for _ in range(4):
-                model.step(tok, args.effort)
-                torch.cuda.synchronize()
+            tp_check = {"tokens": 4}
+            ok = [True]
+            for eff, key in ((1.0, "logit_cos_sim_vs_unsharded_effort_1.0"), (args.effort, f"logit_cos_sim_vs_unsharded_effort_{args.effort}")):
+                model.reset()
+                cs_tp = []
+                tok = torch.tensor([1], dtype=torch.int32, device="cuda")
                 if rank == 0:
-                    ref_model.step(tok, args.effort)
+                    ref_model.reset()
+                for _ in range(4):
+                    model.step(tok, eff)
                     torch.cuda.synchronize()
-                    a, b = model.logits().double(), ref_model.logits().double()
-                    cs_tp.append(float((a @ b) / (a.norm() * b.norm())))
-                    tok = torch.tensor([ref_model.next_token()], dtype=torch.int32, device="cuda")
-                tl = [int(tok.item())]
-                dist.broadcast_object_list(tl, src=0)
-                tok = torch.tensor(tl, dtype=torch.int32, device="cuda")
+                    if rank == 0:
+                        ref_model.step(tok, eff)
+                        torch.cuda.synchronize()
+                        a, b = model.logits().double(), ref_model.logits().double()
+                        cs_tp.append(float((a @ b) / (a.norm() * b.norm())))
+                        tok = torch.tensor([ref_model.next_token()], dtype=torch.int32, device="cuda")
+                    tl = [int(tok.item())]
+                    dist.broadcast_object_list(tl, src=0)
+                    tok = torch.tensor(tl, dtype=torch.int32, device="cuda")
+                tp_check[key] = cs_tp
+                if rank == 0 and eff == 1.0:
+                    ok[0] = min(cs_tp) > 0.9995
+            dist.broadcast_object_list(ok, src=0)      # every rank leaves together: a lone assert would strand the peers
+            if not ok[0]:
+                if rank == 0:
+                    print(json.dumps({"error": "tensor-parallel logits diverge from the unsharded model", "tp_check": tp_check}))
+                dist.destroy_process_group()
+                raise SystemExit(3)
             if rank == 0:
-                tp_check = {"logit_cos_sim_vs_unsharded": cs_tp, "tokens": 4}
-                assert min(cs_tp) > 0.99, f"tensor-parallel logits diverge from the unsharded model: {cs_tp}"
                 del ref_model
                 torch.cuda.empty_cache()
+            model.reset()
 
         # roofline of the dominant operator: bucketMul 4096 -> 14336 (w1/w3; 50 % of the bucket bytes with w2)
         roof = None

@@ -64,7 +64,7 @@ def _collectives_worker(rank, world, port, replays):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=stream):
             enqueue()
-        done = 2
+        done = 1                                     # capture records the update, it does not run it
         for k in range(replays):
             g.replay()
             done += 1
