@@ -108,7 +108,8 @@ attention_kernel(const float* __restrict__ xq, const float* __restrict__ xk, con
                  const int* __restrict__ pos_dev, int n_heads, int n_kv, float theta, int max_seq,
                  float* __restrict__ attn_out, const ZeroList zl) {
     constexpr int HD = 128;
-    __shared__ float q[HD];
+    __shared__ __align__(16) float q[HD];
+    __shared__ __align__(16) float kcur[HD];  // this token's roped key (every head keeps its own copy: no cross-CTA wait)
     __shared__ float acc_s[8][HD];
     __shared__ float sum_s[8];
     const int h = blockIdx.x, kvh = h / (n_heads / n_kv);
@@ -118,17 +119,20 @@ attention_kernel(const float* __restrict__ xq, const float* __restrict__ xk, con
     pos = pos < 0 ? 0 : (pos >= max_seq ? max_seq - 1 : pos);  // backstop: the host refuses steps past max_seq
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     zero_lists(zl, blockIdx.x, gridDim.x, tid, blockDim.x);
-    // rope(q) into smem; the first head of each KV group also ropes k and appends k/v to the cache
+    // rope(q) and rope(k) into smem; the first head of each KV group also appends k/v to the cache
     if (tid < HD) {
         const int j = tid & 63;
         const float freq = powf(1e-6f * (1e6f / theta), (float)j / 64.f);  // theta=1e6 -> 1e-6^(j/64)
         const float ang = (float)pos * freq;
         const float c = cosf(ang), s = sinf(ang);
         const float* qh = xq + (size_t)h * HD;
-        q[tid] = (tid < 64) ? qh[tid] * c - qh[tid + 64] * s : qh[tid] * c + qh[tid - 64] * s;
+        const float* kh = xk + (size_t)kvh * HD;
+        const float qa = qh[tid], qb = (tid < 64) ? qh[tid + 64] : qh[tid - 64];
+        const float ka = kh[tid], kb = (tid < 64) ? kh[tid + 64] : kh[tid - 64];
+        q[tid] = (tid < 64) ? qa * c - qb * s : qa * c + qb * s;
+        const float kr = (tid < 64) ? ka * c - kb * s : ka * c + kb * s;
+        kcur[tid] = kr;
         if (h % (n_heads / n_kv) == 0) {
-            const float* kh = xk + (size_t)kvh * HD;
-            const float kr = (tid < 64) ? kh[tid] * c - kh[tid + 64] * s : kh[tid] * c + kh[tid - 64] * s;
             kcache[((size_t)pos * n_kv + kvh) * HD + tid] = kr;
             vcache[((size_t)pos * n_kv + kvh) * HD + tid] = xv[(size_t)kvh * HD + tid];
         }
@@ -138,31 +142,34 @@ attention_kernel(const float* __restrict__ xq, const float* __restrict__ xk, con
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float sum = 0.f;
     const float scale = rsqrtf((float)HD);
-    for (int t = warp; t <= pos; t += 8) {
-        float4 k4, v4;
-        if (t == pos) {  // the entry this token appends: written by another CTA of the group, read the source
-            const int j0 = lane * 4;
-            float kk[4];
+    // warp w takes tokens w, w+8, ...; four of them per step so that eight 16-byte loads are in flight (the loop is a chain
+    // of L2 round trips otherwise).  The entry this token appends is read from its source, not from the cache another CTA
+    // of the group is writing.  Same summation order as one token per step.
+    for (int tb = warp; tb <= pos; tb += 32) {
+        float4 k4[4], v4[4];
 #pragma unroll
-            for (int d = 0; d < 4; d++) {
-                const int x = j0 + d, j = x & 63;
-                const float freq = powf(1e-6f * (1e6f / theta), (float)j / 64.f);
-                const float ang = (float)pos * freq;
-                const float c = cosf(ang), s = sinf(ang);
-                const float* kh = xk + (size_t)kvh * HD;
-                kk[d] = (x < 64) ? kh[x] * c - kh[x + 64] * s : kh[x] * c + kh[x - 64] * s;
+        for (int i = 0; i < 4; i++) {
+            const int t = tb + 8 * i;
+            k4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            v4[i] = k4[i];
+            if (t < pos) {
+                k4[i] = *reinterpret_cast<const float4*>(kcache + ((size_t)t * n_kv + kvh) * HD + lane * 4);
+                v4[i] = *reinterpret_cast<const float4*>(vcache + ((size_t)t * n_kv + kvh) * HD + lane * 4);
+            } else if (t == pos) {
+                k4[i] = *reinterpret_cast<const float4*>(&kcur[lane * 4]);
+                v4[i] = *reinterpret_cast<const float4*>(xv + (size_t)kvh * HD + lane * 4);
             }
-            k4 = make_float4(kk[0], kk[1], kk[2], kk[3]);
-            v4 = *reinterpret_cast<const float4*>(xv + (size_t)kvh * HD + j0);
-        } else {
-            k4 = *reinterpret_cast<const float4*>(kcache + ((size_t)t * n_kv + kvh) * HD + lane * 4);
-            v4 = *reinterpret_cast<const float4*>(vcache + ((size_t)t * n_kv + kvh) * HD + lane * 4);
         }
-        float d = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
-        d = warp_sum_f(d);
-        const float p = expf(d * scale);
-        sum += p;
-        acc.x += p * v4.x; acc.y += p * v4.y; acc.z += p * v4.z; acc.w += p * v4.w;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (tb + 8 * i <= pos) {
+                float d = q4.x * k4[i].x + q4.y * k4[i].y + q4.z * k4[i].z + q4.w * k4[i].w;
+                d = warp_sum_f(d);
+                const float p = expf(d * scale);
+                sum += p;
+                acc.x += p * v4[i].x; acc.y += p * v4[i].y; acc.z += p * v4[i].z; acc.w += p * v4[i].w;
+            }
+        }
     }
     *reinterpret_cast<float4*>(&acc_s[warp][lane * 4]) = acc;
     if (lane == 0) sum_s[warp] = sum;
@@ -295,8 +302,7 @@ head_kernel(const float* __restrict__ h, const __half* __restrict__ norm_w, floa
     for (int o = blockIdx.x * 8 + warp; o < out; o += gridDim.x * 8) {
         const __half* row = W + (size_t)o * in;
         float acc = 0.f;
-        for (int c = lane * 8; c < in; c += 256) {
-            const uint4 d = ldg_stream_u4(row + c);
+        auto mac8 = [&](const uint4 d, int c) {
             const uint32_t ws[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -304,6 +310,15 @@ head_kernel(const float* __restrict__ h, const __half* __restrict__ norm_w, floa
                 acc = fmaf(vs[c + 2 * j], f.x, acc);
                 acc = fmaf(vs[c + 2 * j + 1], f.y, acc);
             }
+        };
+        if (in == 4096) {  // the whole 8 KB row in flight before the first multiply (same summation order)
+            uint4 d[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) d[k] = ldg_stream_u4(row + lane * 8 + 256 * k);
+#pragma unroll
+            for (int k = 0; k < 16; k++) mac8(d[k], lane * 8 + 256 * k);
+        } else {
+            for (int c = lane * 8; c < in; c += 256) mac8(ldg_stream_u4(row + c), c);
         }
         acc = warp_sum_f(acc);
         if (lane == 0) logits[o] = acc;

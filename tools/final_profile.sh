@@ -12,6 +12,7 @@ for e in 0.25 1.0; do
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:bucket_mul_v4 -s 20 -c 1 -f -o $O/r02_v4_e$e python tools/prof_one.py --shape 4096x14336 --effort $e --n 24 > $O/r02_ncu_full_$e.log 2>&1
   EFFORT_TRACE=1 timeout 120 python tools/trace_v2.py --shape 4096x14336 --effort $e 2>&1 | tail -40 > $O/r02_timeline_e$e.txt
 done
+make -s -C tools/ubench all > /dev/null 2>&1
 timeout 60 tools/ubench/acc_rate > $O/r02_ubench_acc_rate.txt 2>&1
 timeout 60 tools/ubench/stage_cost > $O/r02_ubench_stage_cost.txt 2>&1
 timeout 60 tools/ubench/stream_acc > $O/r02_ubench_stream_acc.txt 2>&1
