@@ -78,6 +78,7 @@ struct V2Batch {
     int ring_bytes;          // bucket_mul_v3_kernel: bytes of the producer's staging ring
     int prefetch;            // bucket_mul_v4_kernel: speculative L2 prefetch of the rows the hint selects
     int lookahead;           // bucket_mul_v4_kernel: consumers test the next unit's barrier / fetch its descriptor early
+    int trace_cycles;        // EFFORT_TRACE=2: only the cheap SM-cycle stamps (the global-timer stamps perturb the phases)
     int window;              // bucket_mul_v4_kernel (bulk): most units a producer takes per ticket grab (1..8)
     int cta_begin[kMulBatchMax + 1];
     V2Problem p[kMulBatchMax];
@@ -144,7 +145,7 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 
 #define V2_TRACE(k)                                                                              \
     do {                                                                                         \
-        if (pb.trace && threadIdx.x == 0) pb.trace[(size_t)blockIdx.x * 16 + (k)] = gtime_ns(); \
+        if (pb.trace && !batch.trace_cycles && threadIdx.x == 0) pb.trace[(size_t)blockIdx.x * 16 + (k)] = gtime_ns(); \
     } while (0)
 
 // ---- exact cutoff: (k+1)-th largest of the 4096 bf16 probe products ------------------------------------------------

@@ -186,6 +186,9 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
     if (pb.exp_no) pdl_wait();
     const uint32_t e_no = pb.exp_no ? *pb.exp_no : 0u;
     V2_TRACE(0);
+    // EFFORT_TRACE: SM-cycle stamps of the prologue phases of CTA 0, thread 0 (cheap, unlike the global timer)
+    unsigned long long* cst = (pb.trace && blockIdx.x == 0 && tid == 0) ? pb.trace + (size_t)kNumSMs * 16 + 696 : nullptr;
+    if (cst) cst[0] = (unsigned long long)clock64();
 
     // ---- 0. constant metadata before the dependency wait ----
     const uint64_t keep = l2_policy_evict_last();
@@ -235,6 +238,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
     }
     V2_TRACE(1);
     pdl_wait();
+    if (cst) cst[1] = (unsigned long long)clock64();
 
     // ---- 1. inputs.  Select group: 32 entries per thread for the cutoff; everybody: the thread's own input dim ----
     const int slice_cols = min(pb.W, C - slice * pb.W);
@@ -326,6 +330,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                 keys[4 * c] = k4[0]; keys[4 * c + 1] = k4[1]; keys[4 * c + 2] = k4[2]; keys[4 * c + 3] = k4[3];
             }
             V2_TRACE(3);
+            if (cst) cst[2] = (unsigned long long)clock64();
             uint32_t hint_key = 0u;
             if (pb.cutoff_hint) {  // last cutoff of this matrix (kVNorm: stored times that call's denominator)
                 const float hc = pb.cutoff_hint[e_no] / denom;
@@ -355,6 +360,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
         }
     }
     V2_TRACE(2);
+    if (cst) cst[3] = (unsigned long long)clock64();
     float denom = 1.f;
     if constexpr (CUT != kCutSelect) {
         // bit-exact replay of the reference's bisection by four warps (cutoff.cuh)
@@ -387,6 +393,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
         }
     }
     __syncthreads();  // cutoff and denominator known; tiles zeroed; barriers initialised
+    if (cst) cst[4] = (unsigned long long)clock64();
     const float cutoff = hdr.cutoff;
     if (vmode == kVNorm) {
         denom = hdr.denom;
@@ -394,6 +401,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
     } else if (vmode == kVSilu) {
         my_v = silu_mul(my_v, my_x3);
     }
+    if (cst) cst[10] = (unsigned long long)clock64();
     if (pb.cutoff_out && lb == 0 && tid == 0) *pb.cutoff_out = cutoff;
     if (pb.cutoff_hint && lb == 0 && tid == 0) pb.cutoff_hint[e_no] = cutoff * (vmode == kVNorm ? denom : 1.f);
     V2_TRACE(6);
@@ -419,6 +427,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
     const uint32_t full0 = (uint32_t)__cvta_generic_to_shared(&hdr.full_bar[pair][0]);
     const uint32_t empty0 = (uint32_t)__cvta_generic_to_shared(&hdr.empty_bar[pair][0]);
     const uint32_t desc0 = (uint32_t)__cvta_generic_to_shared(&hdr.desc[pair][0]);
+    if (cst) cst[11] = (unsigned long long)clock64();
     bool pristine = true;  // ticket / n_units still at their initial zero
     // ---- passes over the inputs of this row split (one pass for every Mistral shape) ----
     for (int j0 = 0; j0 < n_in; j0 += NT) {
@@ -437,14 +446,23 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
             }
         }
         // 2. selection mask of this thread's input (prepareDispatch, bucketMul.metal:66)
+        // The prologue is ISSUE bound (all sixteen warps run the same straight-line code: 4 warps per scheduler), so warps
+        // whose 32 inputs lie past n_in skip it.  No per-row guards: statistics of ranks >= P and inputs past n_in are
+        // zero, and `cutoff < 0` never holds.
+        const bool warp_has_inputs = j0 + warp * 32 < n_in;
         unsigned m = 0u;
+        if (cst && j0 == 0) cst[12] = (unsigned long long)clock64();
+        if (warp_has_inputs) {
 #pragma unroll
-        for (int rho = 0; rho < 16; rho++)
-            if (rho < P && j < n_in && row_selected(cutoff, sel_stat[rho], my_v)) m |= 1u << rho;
-        if (pb.sel_counts) {
-            const int wrows = __reduce_add_sync(0xffffffffu, __popc(m));
-            if (lane == 0 && wrows) atomicAdd(&hdr.sel_rows, wrows);
+            for (int rho = 0; rho < 16; rho++)
+                if (row_selected(cutoff, sel_stat[rho], my_v)) m |= 1u << rho;
+            if (cst && j0 == 0) cst[13] = (unsigned long long)clock64();
+            if (pb.sel_counts) {
+                const int wrows = __reduce_add_sync(0xffffffffu, __popc(m));
+                if (lane == 0 && wrows) atomicAdd(&hdr.sel_rows, wrows);
+            }
         }
+        if (cst && j0 == 0) cst[5] = (unsigned long long)clock64();
         const uint32_t my_src = (uint32_t)(((size_t)e_no * pb.in * P * C + (size_t)(rsp + j * RS) * P * slice_cols) >> 3);
         const float my_val = pb.out_scale ? my_v * *pb.out_scale : my_v;  // the selection above used the unscaled input
         // ---- rounds: every input contributes its next maximal run of selected ranks as one unit.  Bucket statistics fall
@@ -458,7 +476,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                 __syncthreads();
             }
             pristine = false;
-            {   // 2b. the unit list: order is irrelevant, so a warp reserves its records with one shared-memory atomic
+            if (warp_has_inputs) {  // 2b. the unit list: order is irrelevant, so a warp reserves its records with one shared-memory atomic
                 const unsigned bal = __ballot_sync(0xffffffffu, m != 0u);
                 unsigned base = 0u;
                 if (lane == 0 && bal) base = atomicAdd(&hdr.n_units, (unsigned)__popc(bal));
@@ -471,7 +489,9 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                         make_uint4(my_src + (uint32_t)st * rs16, (uint32_t)len, __float_as_uint(my_val), 0u);
                 }
             }
+            if (cst && j0 == 0) cst[6] = (unsigned long long)clock64();
             more = __syncthreads_or(m != 0u) != 0;
+            if (cst && j0 == 0) cst[7] = (unsigned long long)clock64();
             V2_TRACE(8);
 
             if (!consumer && BULK) {
@@ -698,6 +718,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
     __syncthreads();
     if (pb.sel_counts && slice == 0 && tid == 0) pb.sel_counts[rsp] = (uint32_t)hdr.sel_rows;
     V2_TRACE(9);
+    if (cst) cst[8] = (unsigned long long)clock64();
 
     // ---- 4. CTA epilogue: sum the 8 consumer tiles and add into out ----
     {
@@ -742,6 +763,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
             }
         }
     }
+    if (cst) cst[9] = (unsigned long long)clock64();
     V2_TRACE(10);
 }
 

@@ -164,8 +164,8 @@ extern "C" int effort_ctx_create(int device, effort_ctx_t** ctx_out) {
     { const char* e = getenv("EFFORT_WINDOW"); if (e && atoi(e) >= 1 && atoi(e) <= 8) c->window = atoi(e); }
     { const char* e = getenv("EFFORT_HINT"); if (e) c->use_hint = atoi(e) ? 1 : 0; }
     if (getenv("EFFORT_TRACE")) {
-        CK(cudaMalloc(&c->trace, sizeof(unsigned long long) * (16 * c->n_sms + 648 + 48)));
-        CK(cudaMemset(c->trace, 0, sizeof(unsigned long long) * (16 * c->n_sms + 648 + 48)));
+        CK(cudaMalloc(&c->trace, sizeof(unsigned long long) * (16 * c->n_sms + 648 + 48 + 16)));
+        CK(cudaMemset(c->trace, 0, sizeof(unsigned long long) * (16 * c->n_sms + 648 + 48 + 16)));
     }
     *ctx_out = c;
     return EFFORT_OK;
@@ -201,8 +201,8 @@ extern "C" int effort_ctx_error_flag(effort_ctx_t* c, unsigned* flag_out, void* 
 extern "C" int effort_debug_read_unit_trace(effort_ctx_t* c, unsigned long long* host648) {
     if (!c || !c->trace || !host648) return EFFORT_EINVAL;
     CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(host648, c->trace + 16 * c->n_sms, sizeof(unsigned long long) * (648 + 48), cudaMemcpyDeviceToHost));
-    CK(cudaMemset(c->trace + 16 * c->n_sms, 0, sizeof(unsigned long long) * (648 + 48)));
+    CK(cudaMemcpy(host648, c->trace + 16 * c->n_sms, sizeof(unsigned long long) * (648 + 48 + 16), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(c->trace + 16 * c->n_sms, 0, sizeof(unsigned long long) * (648 + 48 + 16)));
     return EFFORT_OK;
 }
 
@@ -555,6 +555,7 @@ static int launch_v2_batch(effort_ctx* ctx, const V2Call* calls, int n, int slot
     batch.dynamic = ctx->dynamic;
     batch.prefetch = ctx->prefetch;
     batch.window = ctx->window;
+    { static const int tc = [] { const char* e = getenv("EFFORT_TRACE"); return e && atoi(e) == 2 ? 1 : 0; }(); batch.trace_cycles = tc; }
     batch.lookahead = ctx->lookahead;
     const size_t smem = L::bytes(batch.list_cap, D);
     if (smem > kMaxSmem) return EFFORT_ESHAPE;
@@ -564,7 +565,9 @@ static int launch_v2_batch(effort_ctx* ctx, const V2Call* calls, int n, int slot
         static std::map<std::pair<int, const void*>, bool> configured;
         const auto key = std::make_pair(ctx->device, (const void*)kernel);
         if (!configured.count(key)) {
-            CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+            cudaFuncAttributes fa{};
+            CK(cudaFuncGetAttributes(&fa, kernel));  // static shared memory counts against the same 227 KB
+            CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxSmem - fa.sharedSizeBytes)));
             configured[key] = true;
         }
         CK(launch_pdl(kernel, dim3(cta), dim3(threads), smem_bytes, stream, batch));

@@ -1,7 +1,7 @@
 """Phase timeline of bucket_mul_v2_kernel (EFFORT_TRACE=1): per-CTA globaltimer stamps of one isolated launch."""
 import argparse, ctypes as C, os, sys
 import numpy as np
-os.environ["EFFORT_TRACE"] = "1"
+os.environ.setdefault("EFFORT_TRACE", "1")
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -36,16 +36,22 @@ for rep in range(3):
     n = L.effort_debug_read_trace(ctx._h, buf.ctypes.data, 148)
     t = buf[:n].astype(np.int64)
     t = t[t[:, 0] > 0]
+    if len(t) == 0:          # EFFORT_TRACE=2: cycle stamps only
+        t = np.zeros((1, 16), dtype=np.int64)
     t0 = t[:, 0].min()
     print(f"{a.shape} effort {a.effort} rep {rep}: event total {s.elapsed_time(e)*1000:.1f} us; ctas {len(t)}; selected {ops.lastSelected()}")
     for k, nm in names.items():
         rel = (t[:, k] - t0) / 1000.0
         print(f"   {nm:10s} min {rel.min():7.2f}  median {np.median(rel):7.2f}  max {rel.max():7.2f} us")
-    ub = np.zeros(648 + 48, dtype=np.uint64)
+    ub = np.zeros(648 + 48 + 16, dtype=np.uint64)
     if L.effort_debug_read_unit_trace(ctx._h, ub.ctypes.data) == 0 and rep == 2:
         base = int(ub[640])
         u = ub[:640].reshape(80, 8).astype(np.int64)
-        fin = ub[648:].astype(np.int64)
+        cs = ub[696:710].astype(np.int64)
+        lab = ["entry", "dependency wait over", "products scored", "select done", "cutoff broadcast", "masks", "records stored",
+               "list barrier", "consumers done", "tiles reduced", "(v normalised", "constants", "loop top", "16 tests)"]
+        print("   CTA 0 thread 0, SM cycles since kernel entry: " + "; ".join(f"{l} {int(c - cs[0])}" for l, c in zip(lab, cs) if c))
+        fin = ub[648:696].astype(np.int64)
         print("   consumers of CTA 0: ran dry at cycle / rows / units:",
               "  ".join(f"{int(fin[w]) - base if fin[w] else -1}/{int(fin[16 + w])}/{int(fin[32 + w])}" for w in range(8)))
         print("   units of pair 0, CTA 0 -- SM cycles since the CTA started: rows | producer issued | consumer: starts waiting, "
