@@ -15,7 +15,7 @@
 //    mbarrier (cp.async.mbarrier.arrive.noinc), the slot comes back through a second one.  Units are whole inputs, so
 //    the per-unit cost is paid once per ~6 rows at effort 0.25 and once per 16 rows at effort 1.0, no list is built,
 //    and up to 8 x 4 x 4 KB are in flight per SM.
-//  * the exact-select cutoff runs on FOUR warps (one per scheduler, 32 products per lane, a 128-thread named barrier
+//  * the exact-select cutoff runs on the EIGHT consumer warps (two per scheduler, 16 products per lane, a 256-thread named barrier
 //    per round) while the other twelve zero the tiles, fetch their stats and inputs and run the overwrite protocol.
 #pragma once
 #include "bucket_mul_v3.cuh"
@@ -25,7 +25,10 @@ namespace effort {
 constexpr int kV4Pairs = 8;                    // consumer / producer warp pairs
 constexpr int kV4Units = 16;                   // units in flight per pair (descriptor slots; a power of two)
 constexpr int kV4RingBytes = 16 * 1024;        // staging bytes per pair: a first-in-first-out byte ring
-constexpr int kV4SelWarps = 4;
+constexpr int kV4SelWarps = 8;                                   // warps of the exact-select group (the consumers)
+constexpr int kSelVals = EFFORT_PROBES_MAX / (kV4SelWarps * 32);  // probe products per thread (16)
+constexpr int kSelKeys = kSelVals / 2, kSelChunks = kSelVals / 8; // packed bf16x2 registers; 8-value chunks
+static_assert(kSelVals * kV4SelWarps * 32 == EFFORT_PROBES_MAX && kSelChunks >= 1, "the group holds all 4096 products");
 
 struct __align__(16) V4Desc {
     uint32_t off;      // byte offset of the unit's first row in the pair's ring
@@ -87,16 +90,16 @@ __device__ __forceinline__ float div_by(float x, float d, float r) {
     return fmaf(fmaf(-q, d, x), r, q);
 }
 
-// count of keys above the threshold, 32 keys (16 bf16x2 registers) per thread
-__device__ __forceinline__ uint32_t count_gt32(const uint32_t (&keys)[16], uint32_t th) {
+// count of keys above the threshold, kSelVals keys (kSelKeys bf16x2 registers) per thread
+__device__ __forceinline__ uint32_t count_gt32(const uint32_t (&keys)[kSelKeys], uint32_t th) {
     const __nv_bfloat162 t = as_bf162(splat_bf16(th));
     __nv_bfloat162 c0 = __hgt2(as_bf162(keys[0]), t), c1 = __hgt2(as_bf162(keys[1]), t);
 #pragma unroll
-    for (int i = 2; i < 16; i += 2) {
+    for (int i = 2; i < kSelKeys; i += 2) {
         c0 = __hadd2(c0, __hgt2(as_bf162(keys[i]), t));
         c1 = __hadd2(c1, __hgt2(as_bf162(keys[i + 1]), t));
     }
-    return (uint32_t)bf162_count(__hadd2(c0, c1));  // 0..32
+    return (uint32_t)bf162_count(__hadd2(c0, c1));  // 0..kSelVals
 }
 
 // Exact select on the first kV4SelWarps warps (gt = thread index inside the group).  Q(x) = [#{keys > x} >= k+1] is true
@@ -106,7 +109,7 @@ __device__ __forceinline__ uint32_t count_gt32(const uint32_t (&keys)[16], uint3
 // rounds from scratch.  With a hint -- the key of the cutoff this matrix saw on the previous call -- the first round
 // brackets it (hint +- 16 keys = +- 12 % in value) and two more rounds finish when the guess holds; a miss only costs the
 // bracketing round.  The result does not depend on the hint.
-__device__ __forceinline__ float select_cutoff_group(const uint32_t (&keys)[16], int k, V4Header& hdr, int gt, uint32_t hint_key,
+__device__ __forceinline__ float select_cutoff_group(const uint32_t (&keys)[kSelKeys], int k, V4Header& hdr, int gt, uint32_t hint_key,
                                                      int* rounds_out) {
     const int lane = gt & 31, gw = gt >> 5;
     const unsigned need = (unsigned)(k + 1);
@@ -216,15 +219,15 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
     };
     if (tid < n_in) load_stats(tid, sel_stat);
     const int vmode = pb.norm_w ? kVNorm : (pb.v2 ? kVSilu : kVPlain);
-    uint4 prb[4], nwv[4];
-    if (CUT == kCutSelect && sel_warp) {  // 32 consecutive probes (and norm weights) per thread of the select group
-        const uint4* pp = reinterpret_cast<const uint4*>(pb.probes + (size_t)e_no * EFFORT_PROBES_MAX) + 4 * tid;
+    uint4 prb[kSelChunks], nwv[kSelChunks];
+    if (CUT == kCutSelect && sel_warp) {  // kSelVals consecutive probes (and norm weights) per thread of the select group
+        const uint4* pp = reinterpret_cast<const uint4*>(pb.probes + (size_t)e_no * EFFORT_PROBES_MAX) + kSelChunks * tid;
 #pragma unroll
-        for (int c = 0; c < 4; c++) prb[c] = ldg_keep_u4(pp + c, keep);
+        for (int c = 0; c < kSelChunks; c++) prb[c] = ldg_keep_u4(pp + c, keep);
         if (vmode == kVNorm) {
-            const uint4* np4 = reinterpret_cast<const uint4*>(pb.norm_w) + 4 * tid;
+            const uint4* np4 = reinterpret_cast<const uint4*>(pb.norm_w) + kSelChunks * tid;
 #pragma unroll
-            for (int c = 0; c < 4; c++) nwv[c] = np4[c];
+            for (int c = 0; c < kSelChunks; c++) nwv[c] = np4[c];
         }
     }
     if (warp == NC) {  // first producer warp: the ring barriers
@@ -240,7 +243,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
     pdl_wait();
     if (cst) cst[1] = (unsigned long long)clock64();
 
-    // ---- 1. inputs.  Select group: 32 entries per thread for the cutoff; everybody: the thread's own input dim ----
+    // ---- 1. inputs.  Select group: kSelVals entries per thread for the cutoff; everybody: the thread's own input dim ----
     const int slice_cols = min(pb.W, C - slice * pb.W);
     float my_v = 0.f, my_x3 = 0.f, my_nw = 1.f;
     if (tid < n_in) {
@@ -270,7 +273,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
         auto raw = [&](float x, float x3, float nw) { return vmode == kVSilu ? silu_mul(x, x3) : (vmode == kVNorm ? x * nw : x); };
         if (tid < n_in) spec(tid, sel_stat, raw(my_v, my_x3, my_nw));
         if (CUT == kCutSelect && tid >= kV4SelWarps * 32 && tid < 2 * kV4SelWarps * 32 && tid - kV4SelWarps * 32 < n_in) {
-            const int j2 = tid - kV4SelWarps * 32;  // the select warps' inputs: covered by the next four warps
+            const int j2 = tid - kV4SelWarps * 32;  // the select warps' inputs: covered by the other warps
             float st2[16];
 #pragma unroll
             for (int rho = 0; rho < 16; rho++) st2[rho] = 0.f;
@@ -282,16 +285,16 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
     if constexpr (CUT == kCutSelect) {
         if (sel_warp) {
             const float* src = (vmode == kVPlain) ? pb.v_cut : pb.v;
-            float vv[32];
+            float vv[kSelVals];
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const float4 a = *reinterpret_cast<const float4*>(src + 32 * tid + 4 * c);
+            for (int c = 0; c < kSelVals / 4; c++) {
+                const float4 a = *reinterpret_cast<const float4*>(src + kSelVals * tid + 4 * c);
                 vv[4 * c] = a.x; vv[4 * c + 1] = a.y; vv[4 * c + 2] = a.z; vv[4 * c + 3] = a.w;
             }
             if (vmode == kVSilu) {
 #pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    const float4 a = *reinterpret_cast<const float4*>(pb.v2 + 32 * tid + 4 * c);
+                for (int c = 0; c < kSelVals / 4; c++) {
+                    const float4 a = *reinterpret_cast<const float4*>(pb.v2 + kSelVals * tid + 4 * c);
                     vv[4 * c] = silu_mul(vv[4 * c], a.x); vv[4 * c + 1] = silu_mul(vv[4 * c + 1], a.y);
                     vv[4 * c + 2] = silu_mul(vv[4 * c + 2], a.z); vv[4 * c + 3] = silu_mul(vv[4 * c + 3], a.w);
                 }
@@ -300,7 +303,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
             if (vmode == kVNorm) {  // rmsNorm32fast (aux.metal:113-152) over the 4096 entries the group holds
                 float ss = 0.f;
 #pragma unroll
-                for (int m = 0; m < 32; m++) ss += vv[m] * vv[m];
+                for (int m = 0; m < kSelVals; m++) ss += vv[m] * vv[m];
                 ss = warp_sum_f(ss);
                 if (lane == 0) hdr.red[warp] = ss;
                 asm volatile("bar.sync 2, %0;" ::"n"(kV4SelWarps * 32) : "memory");
@@ -311,7 +314,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                 if (tid == 0) hdr.denom = denom;
                 const float rden = __frcp_rn(denom);
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
+                for (int c = 0; c < kSelChunks; c++) {
                     const uint32_t nw[4] = {nwv[c].x, nwv[c].y, nwv[c].z, nwv[c].w};
 #pragma unroll
                     for (int m = 0; m < 4; m++) {
@@ -321,9 +324,9 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                     }
                 }
             }
-            uint32_t keys[16];
+            uint32_t keys[kSelKeys];
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
+            for (int c = 0; c < kSelChunks; c++) {
                 const float v8[8] = {vv[8 * c], vv[8 * c + 1], vv[8 * c + 2], vv[8 * c + 3], vv[8 * c + 4], vv[8 * c + 5], vv[8 * c + 6], vv[8 * c + 7]};
                 uint32_t k4[4];
                 score8(v8, prb[c], k4);
