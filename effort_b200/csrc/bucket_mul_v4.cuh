@@ -239,12 +239,37 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
         if (lane == 0) { hdr.ticket = 0u; hdr.n_units = 0u; hdr.sel_rows = 0; }
         // (the __syncthreads before the first use orders the initialisation: no cluster, no async-proxy user here)
     }
+    // Everything the streaming phase needs that does not depend on the input vector is set up HERE, before the dependency
+    // wait: after the cutoff the CTA runs a serial tail (masks, list) at one warp's dependent-issue rate, and every
+    // instruction moved out of it is worth ~4 cycles (EFFORT_TRACE=2 cycle stamps).
+    const int slice_cols = min(pb.W, C - slice * pb.W);
+    const int seg_bytes = slice_cols * 2;
+    const bool full_width = slice_cols == TW;
+    const int lpr = pb.lpr, R = pb.R;
+    const uint32_t base_lane = (tiles_saddr + (uint32_t)pair * V4Smem::kTileBytes) | (uint32_t)(lane * 4);
+    const uint64_t pol = l2_policy_evict_first();
+    const uint4* bk16 = reinterpret_cast<const uint4*>(pb.bk + (size_t)pb.in * P * ((size_t)slice * pb.W));  // slice-major
+    const uint32_t rs16 = (uint32_t)(seg_bytes >> 4);
+    // first 16-byte piece of local input j's rank-0 row slice, relative to bk16
+    auto src_of = [&](int j) { return (uint32_t)(((size_t)e_no * pb.in * P * C + (size_t)(rsp + j * RS) * P * slice_cols) >> 3); };
+    const uint32_t my_src0 = src_of(tid);
+
+    // debugging aid (EFFORT_TRACE): issue / arrival / release times of the first 80 units of pair 0 of CTA 0
+    unsigned long long* utrace = (pb.trace && blockIdx.x == 0 && pair == 0) ? pb.trace + (size_t)kNumSMs * 16 : nullptr;
+    if (utrace && tid == 0) utrace[640] = (unsigned long long)clock64();  // time base: the SM's cycle counter
+    // pair state.  Both sides count units (seq); unit s uses descriptor slot s % kV4Units, barrier phase (s / kV4Units) & 1.
+    // Producer only: ring head, free bytes, oldest unit not yet reclaimed.
+    uint32_t seq = 0, tail_seq = 0, head = 0, free_b = kV4RingBytes;
+    uint32_t slot_charged = 0u;  // bulk producers: lane s remembers the ring bytes the unit in descriptor slot s holds
+    const uint32_t ticket_saddr = (uint32_t)__cvta_generic_to_shared(&hdr.ticket);
+    const uint32_t full0 = (uint32_t)__cvta_generic_to_shared(&hdr.full_bar[pair][0]);
+    const uint32_t empty0 = (uint32_t)__cvta_generic_to_shared(&hdr.empty_bar[pair][0]);
+    const uint32_t desc0 = (uint32_t)__cvta_generic_to_shared(&hdr.desc[pair][0]);
     V2_TRACE(1);
     pdl_wait();
     if (cst) cst[1] = (unsigned long long)clock64();
 
     // ---- 1. inputs.  Select group: kSelVals entries per thread for the cutoff; everybody: the thread's own input dim ----
-    const int slice_cols = min(pb.W, C - slice * pb.W);
     float my_v = 0.f, my_x3 = 0.f, my_nw = 1.f;
     if (tid < n_in) {
         const int i = rsp + tid * RS;
@@ -409,27 +434,6 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
     if (pb.cutoff_hint && lb == 0 && tid == 0) pb.cutoff_hint[e_no] = cutoff * (vmode == kVNorm ? denom : 1.f);
     V2_TRACE(6);
 
-    const int seg_bytes = slice_cols * 2;
-    const bool full_width = slice_cols == TW;
-    const int lpr = pb.lpr, R = pb.R;
-    const int rowslot = lane / lpr, lcol = lane % lpr;
-    const bool col_ok = lcol * VEC < slice_cols;
-    const uint32_t base_lane = (tiles_saddr + (uint32_t)pair * V4Smem::kTileBytes) | (uint32_t)(lane * 4);
-    const uint64_t pol = l2_policy_evict_first();
-    const uint4* bk16 = reinterpret_cast<const uint4*>(pb.bk + (size_t)pb.in * P * ((size_t)slice * pb.W));  // slice-major
-    const uint32_t rs16 = (uint32_t)(seg_bytes >> 4);
-
-    // debugging aid (EFFORT_TRACE): issue / arrival / release times of the first 80 units of pair 0 of CTA 0
-    unsigned long long* utrace = (pb.trace && blockIdx.x == 0 && pair == 0) ? pb.trace + (size_t)kNumSMs * 16 : nullptr;
-    if (utrace && tid == 0) utrace[640] = (unsigned long long)clock64();  // time base: the SM's cycle counter
-    // pair state.  Both sides count units (seq); unit s uses descriptor slot s % kV4Units, barrier phase (s / kV4Units) & 1.
-    // Producer only: ring head, free bytes, oldest unit not yet reclaimed.
-    uint32_t seq = 0, tail_seq = 0, head = 0, free_b = kV4RingBytes;
-    uint32_t slot_charged = 0u;  // bulk producers: lane s remembers the ring bytes the unit in descriptor slot s holds
-    const uint32_t ticket_saddr = (uint32_t)__cvta_generic_to_shared(&hdr.ticket);
-    const uint32_t full0 = (uint32_t)__cvta_generic_to_shared(&hdr.full_bar[pair][0]);
-    const uint32_t empty0 = (uint32_t)__cvta_generic_to_shared(&hdr.empty_bar[pair][0]);
-    const uint32_t desc0 = (uint32_t)__cvta_generic_to_shared(&hdr.desc[pair][0]);
     if (cst) cst[11] = (unsigned long long)clock64();
     bool pristine = true;  // ticket / n_units still at their initial zero
     // ---- passes over the inputs of this row split (one pass for every Mistral shape) ----
@@ -460,13 +464,9 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
             for (int rho = 0; rho < 16; rho++)
                 if (row_selected(cutoff, sel_stat[rho], my_v)) m |= 1u << rho;
             if (cst && j0 == 0) cst[13] = (unsigned long long)clock64();
-            if (pb.sel_counts) {
-                const int wrows = __reduce_add_sync(0xffffffffu, __popc(m));
-                if (lane == 0 && wrows) atomicAdd(&hdr.sel_rows, wrows);
-            }
         }
         if (cst && j0 == 0) cst[5] = (unsigned long long)clock64();
-        const uint32_t my_src = (uint32_t)(((size_t)e_no * pb.in * P * C + (size_t)(rsp + j * RS) * P * slice_cols) >> 3);
+        const uint32_t my_src = (j0 == 0) ? my_src0 : src_of(j);
         const float my_val = pb.out_scale ? my_v * *pb.out_scale : my_v;  // the selection above used the unscaled input
         // ---- rounds: every input contributes its next maximal run of selected ranks as one unit.  Bucket statistics fall
         // with the rank, so a mask is a prefix of the ranks and one round is the normal case; arbitrary statistics (tests)
@@ -479,18 +479,16 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                 __syncthreads();
             }
             pristine = false;
-            if (warp_has_inputs) {  // 2b. the unit list: order is irrelevant, so a warp reserves its records with one shared-memory atomic
-                const unsigned bal = __ballot_sync(0xffffffffu, m != 0u);
-                unsigned base = 0u;
-                if (lane == 0 && bal) base = atomicAdd(&hdr.n_units, (unsigned)__popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
+            if (warp_has_inputs) {
+                // 2b. the unit list: record j of the pass belongs to input j -- no compaction, no atomics on this serial stretch;
+                // an input that selects nothing leaves an empty record (rows = 0) that the producers skip
+                uint32_t st = 0u, len = 0u;
                 if (m) {
-                    const int st = __ffs((int)m) - 1;
-                    const int len = __ffs((int)~(m >> st)) - 1;
+                    st = (uint32_t)__ffs((int)m) - 1u;
+                    len = (uint32_t)__ffs((int)~(m >> st)) - 1u;
                     m &= ~(((1u << len) - 1u) << st);
-                    ulist[base + (unsigned)__popc(bal & ((1u << lane) - 1u))] =
-                        make_uint4(my_src + (uint32_t)st * rs16, (uint32_t)len, __float_as_uint(my_val), 0u);
                 }
+                ulist[tid] = make_uint4(my_src + st * rs16, len, __float_as_uint(my_val), 0u);
             }
             if (cst && j0 == 0) cst[6] = (unsigned long long)clock64();
             more = __syncthreads_or(m != 0u) != 0;
@@ -504,7 +502,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                 // on a WINDOW of units at once, one per lane: one ticket grab (guided: remaining/16, 1..8 units), the records in
                 // parallel, ring space handed out by shuffles, the barrier tests of all outstanding slots in parallel, and each
                 // lane issues its own unit's descriptor + expect_tx + bulk copy. ----
-                const uint32_t nu = hdr.n_units;
+                const uint32_t nu = (uint32_t)min(NT, n_in - j0);  // records of this pass (empty ones included)
                 auto reclaim = [&](bool block) {  // take back the bytes of every unit the consumer has released (in order)
                     const uint32_t out_n = seq - tail_seq;
                     const uint32_t rel = ((uint32_t)lane - tail_seq) & (kV4Units - 1);  // slot `lane`: distance from the oldest
@@ -546,40 +544,38 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                     if (seq != tail_seq) reclaim(false);
 #pragma unroll 1
                     while (pos < cnt) {
-                        // ring space for units pos.. in order (warp-uniform arithmetic on broadcast sizes)
-                        uint32_t h = head, f = free_b, n_ok = 0u, my_off = 0u, my_chg = 0u;
+                        // ring space for the window's records pos.. in order (warp-uniform arithmetic on broadcast sizes); empty
+                        // records are consumed without a slot
+                        uint32_t h = head, f = free_b, n_ok = 0u, n_seen = 0u, my_off = 0u, my_chg = 0u, my_k = 0xffffffffu;
                         const uint32_t slots_free = (uint32_t)kV4Units - (seq - tail_seq);
                         for (uint32_t l = pos; l < cnt; l++) {
                             const uint32_t bts = __shfl_sync(0xffffffffu, my_bytes, (int)l);
+                            if (bts == 0u) { n_seen++; continue; }
                             const uint32_t skip = (h + bts > (uint32_t)kV4RingBytes) ? ((uint32_t)kV4RingBytes - h) : 0u;
                             if (f < bts + skip || n_ok >= slots_free) break;
                             const uint32_t off = skip ? 0u : h;
-                            if ((uint32_t)lane == l) { my_off = off; my_chg = bts + skip; }
+                            if ((uint32_t)lane == l) { my_off = off; my_chg = bts + skip; my_k = n_ok; }
+                            if ((uint32_t)lane == ((seq + n_ok) & (kV4Units - 1))) slot_charged = bts + skip;  // lane s keeps slot s
                             h = off + bts;
                             if (h >= (uint32_t)kV4RingBytes) h = 0u;
                             f -= bts + skip;
                             n_ok++;
+                            n_seen++;
                         }
-                        if (n_ok == 0u) { reclaim(true); continue; }
-                        const uint32_t k = (uint32_t)lane - pos;  // this lane's unit is the k-th of the batch
-                        if ((uint32_t)lane >= pos && k < n_ok) {
-                            const uint32_t slot = (seq + k) & (kV4Units - 1);
+                        if (n_seen == 0u) { reclaim(true); continue; }
+                        if (my_k != 0xffffffffu) {
+                            const uint32_t slot = (seq + my_k) & (kV4Units - 1);
                             const uint32_t fb = full0 + slot * 8u;
                             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(desc0 + slot * 16u), "r"(my_off), "r"(rec.y), "r"(rec.z),
                                          "r"(my_chg) : "memory");
-                            if (utrace && seq + k < 80u) { utrace[8 * (seq + k)] = (unsigned long long)clock64(); utrace[8 * (seq + k) + 3] = (unsigned long long)rec.y; }
+                            if (utrace && seq + my_k < 80u) { utrace[8 * (seq + my_k)] = (unsigned long long)clock64(); utrace[8 * (seq + my_k) + 3] = (unsigned long long)rec.y; }
                             mbar_expect_tx(fb, (int)my_bytes);
                             bulk_g2s(ring_saddr + my_off, bk16 + rec.x, (int)my_bytes, fb, pol);
-                        }
-                        {   // remember what each of the new slots holds (lane s keeps slot s)
-                            const uint32_t rel = ((uint32_t)lane - seq) & (kV4Units - 1);
-                            const uint32_t v = __shfl_sync(0xffffffffu, my_chg, (int)((pos + rel) & 31u));
-                            if (lane < kV4Units && rel < n_ok) slot_charged = v;
                         }
                         seq += n_ok;
                         head = h;
                         free_b = f;
-                        pos += n_ok;
+                        pos += n_seen;
                     }
                 }
                 // stop marker for the consumer
@@ -595,7 +591,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                 }
             } else if (!consumer) {
                 // ---- 3a'. producer of pair `pair`, 16-byte cp.async by all lanes, one unit at a time ----
-                const uint32_t nu = hdr.n_units;
+                const uint32_t nu = (uint32_t)min(NT, n_in - j0);
                 auto grab = [&]() {
                     uint32_t t = 0u;
                     if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(t) : "r"(ticket_saddr) : "memory");
@@ -641,7 +637,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                     if (t >= nu) break;
                     const uint4 rec = ulist[t];
                     tk = grab();  // the next ticket travels while this unit is issued
-                    fill(rec.x, rec.y, rec.z);
+                    if (rec.y != 0u) fill(rec.x, rec.y, rec.z);  // (an input that selected nothing left an empty record)
                 }
                 fill(0u, 0u, 0u);  // stop marker for the consumer
             } else {
@@ -696,6 +692,8 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                             default: break;
                         }
                     } else {  // narrow slice: rows are seg_bytes apart, R rows per step, lanes past the slice idle
+                        const int rowslot = lane / lpr, lcol = lane % lpr;  // (computed here: a division the common path never pays)
+                        const bool col_ok = lcol * VEC < slice_cols;
                         for (int st = 0; st * R < n; st++) {
                             const int r = st * R + rowslot;
                             const bool ok = (rowslot < R) && (r < n) && col_ok;
@@ -709,6 +707,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
                     if (lane == 0) mbar_arrive(eb);
                     if (utrace && lane == 0 && seq <= 80u) utrace[8 * (seq - 1) + 7] = (unsigned long long)clock64();
                 }
+                if (lane == 0 && rows_done) atomicAdd(&hdr.sel_rows, (int)rows_done);  // rows selected = rows accumulated
                 if (pb.trace && blockIdx.x == 0 && lane == 0) {  // when every consumer of CTA 0 ran dry, and how much it did
                     unsigned long long* fin = pb.trace + (size_t)kNumSMs * 16 + 648;
                     fin[warp] = (unsigned long long)clock64();
