@@ -7,16 +7,20 @@
 // prologue has to shrink.
 //
 //  * 8 CONSUMER warps (0-7), each with a private 8 KB accumulator tile, do nothing but wait for a unit, read its rows
-//    and run the read-modify-writes (four rows = 16 independent updates per lane at a time);
-//  * 8 PRODUCER warps (8-15), one per consumer: a producer takes the next input from a shared ticket counter (work
-//    stealing: a consumer that drains faster gets more), looks up its selection mask and -- slice-major layout: the
-//    ranks an input selects inside this CTA's column slice are contiguous -- copies the whole run (1..16 rows) with
-//    16-byte cp.async into the next slot of the pair's private ring; completion reaches the consumer through an
-//    mbarrier (cp.async.mbarrier.arrive.noinc), the slot comes back through a second one.  Units are whole inputs, so
-//    the per-unit cost is paid once per ~6 rows at effort 0.25 and once per 16 rows at effort 1.0, no list is built,
-//    and up to 8 x 4 x 4 KB are in flight per SM.
-//  * the exact-select cutoff runs on the EIGHT consumer warps (two per scheduler, 16 products per lane, a 256-thread named barrier
-//    per round) while the other twelve zero the tiles, fetch their stats and inputs and run the overwrite protocol.
+//    and run the read-modify-writes (four rows = 16 independent updates per lane at a time); while a unit is accumulated
+//    the next slot's barrier is tested and its descriptor fetched;
+//  * 8 PRODUCER warps (8-15), one per consumer.  Units are whole inputs: thread j of the CTA turns input j's selection
+//    mask into record j of a direct-indexed list {first 16-byte piece, rows, multiplier} (slice-major layout: the ranks an
+//    input selects inside this CTA's column slice are contiguous).  BULK (default): a producer takes a WINDOW of records
+//    from a shared ticket counter (guided sizes; work stealing between the pairs), hands out the pair's ring space by
+//    shuffles, tests all outstanding slots' barriers in parallel and lets every lane issue its own unit: descriptor +
+//    mbarrier.arrive.expect_tx + ONE cp.async.bulk of 256..4096 bytes.  !BULK: one unit per step, copied with 16-byte
+//    cp.async by all lanes, completion through cp.async.mbarrier.arrive.noinc.  The slot comes back through a second
+//    mbarrier.  Up to 8 x 16 KB are in flight per SM.
+//  * the exact-select cutoff runs on the EIGHT consumer warps (two per scheduler, 16 products per lane, a 256-thread
+//    named barrier per round) while the producers zero the tiles and run the overwrite protocol.
+//  * what bounds the kernel is the SM's shared-memory pipe (12 wavefronts per 128-weight row: tools/ubench), and at low
+//    effort the serial prologue, which runs at one warp's dependent-issue rate (EFFORT_TRACE=2 cycle stamps): DESIGN.md 4.
 #pragma once
 #include "bucket_mul_v3.cuh"
 
