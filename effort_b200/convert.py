@@ -23,7 +23,9 @@ def q4_convert(core2: torch.Tensor, perc: float = 0.02) -> dict:
     core = core2.clone()
     flat = core.view(-1)
     top = int(flat.numel() * perc)
-    # argsort(-|w|)[:top] (q4_draft.py:79); ties at the 2 % boundary are UNPINNED (numpy quicksort is unstable)
+    # argsort(-|w|)[:top] (q4_draft.py:79); ties at the 2 % boundary are UNPINNED (numpy quicksort is unstable).
+    # One-time convert step, off the hot path: the outlier pick uses the library sort (torch.sort), everything after it
+    # (bucketing, stats, probes) is this repo's kernels (csrc/q4.cuh).
     order = torch.sort(flat.abs().float(), descending=True, stable=True).indices[:top]
     outliers = torch.zeros((top, 4), dtype=torch.float32, device=core.device)
     outliers[:, 0] = flat[order].float()

@@ -48,7 +48,6 @@ struct V4Header {
     float cutoff, denom;
     int sel_rows;
     unsigned ticket;                     // next unit of the list a producer may take
-    unsigned n_units;                    // units in the list
     unsigned long long full_bar[kV4Pairs][kV4Units];
     unsigned long long empty_bar[kV4Pairs][kV4Units];
     V4Desc desc[kV4Pairs][kV4Units];
@@ -240,7 +239,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
             mbar_init((uint32_t)__cvta_generic_to_shared(&hdr.full_bar[0][0] + s), BULK ? 1 : 33);
             mbar_init((uint32_t)__cvta_generic_to_shared(&hdr.empty_bar[0][0] + s), 1);
         }
-        if (lane == 0) { hdr.ticket = 0u; hdr.n_units = 0u; hdr.sel_rows = 0; }
+        if (lane == 0) { hdr.ticket = 0u; hdr.sel_rows = 0; }
         // (the __syncthreads before the first use orders the initialisation: no cluster, no async-proxy user here)
     }
     // Everything the streaming phase needs that does not depend on the input vector is set up HERE, before the dependency
@@ -439,7 +438,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
     V2_TRACE(6);
 
     if (cst) cst[11] = (unsigned long long)clock64();
-    bool pristine = true;  // ticket / n_units still at their initial zero
+    bool pristine = true;  // the ticket counter still at its initial zero
     // ---- passes over the inputs of this row split (one pass for every Mistral shape) ----
     for (int j0 = 0; j0 < n_in; j0 += NT) {
         const int j = j0 + tid;
@@ -479,7 +478,7 @@ bucket_mul_v4_kernel(const __grid_constant__ V2Batch batch) {
         do {
             if (!pristine) {
                 __syncthreads();
-                if (tid == 0) { hdr.ticket = 0u; hdr.n_units = 0u; }
+                if (tid == 0) hdr.ticket = 0u;
                 __syncthreads();
             }
             pristine = false;

@@ -104,9 +104,9 @@ class PythonTensorSaver:
 
 
 class NativeTensorSaver:
-    """TensorSaver over the library's C-ABI writer (effort_saver_*, csrc/safetensors_io.cpp).  Files are written as
-    soon as a layer is complete would need the file count up front (it is part of the file name,
-    safetensors.swift:67), so like the reference the saver collects everything and writes in save()."""
+    """TensorSaver over the library's C-ABI writer (effort_saver_*, csrc/safetensors_io.cpp).  The number of files is
+    part of every file name ("-%05d-of-%05d", safetensors.swift:67), so -- like the reference -- the saver collects the
+    tensors of all layers and writes the shards and the index in save()."""
 
     def __init__(self, path: str, model: str = MODEL_FP16):
         import ctypes as C

@@ -56,8 +56,8 @@ def _fn(lib, pattern):
     return hit[0]
 
 
-def test_default_kernel_streams_with_async_copies(lib):
-    """bucket_mul_v4_kernel<select, cp.async> -- the default path of round 2: weights reach shared memory through LDGSTS
+def test_pairs_kernel_cp_async_variant(lib):
+    """bucket_mul_v4_kernel<select, cp.async> ("pairs-ldgsts", stage 3): weights reach shared memory through LDGSTS
     (16-byte cp.async), completion through ARRIVES.LDGSTSBAR on an mbarrier, the consumer warps wait with
     SYNCS.PHASECHK, results leave as 16-byte vector reductions; no spills, no tensor-core instructions."""
     usage = _run(["--dump-resource-usage"])
@@ -75,6 +75,13 @@ def test_default_kernel_streams_with_async_copies(lib):
     assert "STL" not in sass and "LDL" not in sass
 
 
-def test_bulk_variant_uses_tma_bulk_copies(lib):
+def test_default_kernel_streams_with_bulk_async_copies(lib):
+    """bucket_mul_v4_kernel<select, bulk> -- the default path: one UBLKCP (cp.async.bulk) per unit, completion through the
+    mbarrier's transaction count, 16-byte vector reductions into `out`, packed bf16 counting in the exact select"""
     sass = _run(["-sass", "-fun", _fn(lib, "bucket_mul_v4_kernelILi0ELb1")])
     assert "UBLKCP.S.G" in sass and "LDGSTS" not in sass
+    assert "SYNCS.ARRIVE.TRANS64" in sass and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in sass
+    assert "REDG.E.ADD.F32x4" in sass
+    assert "HSET2.BF16_V2" in sass and "HADD2.BF16_V2" in sass
+    assert not re.search(r"\b(HMMA|IMMA|UTCHMMA|UTCQMMA|QGMMA|HGMMA)\b", sass)
+    assert "STL" not in sass and "LDL" not in sass

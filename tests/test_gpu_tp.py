@@ -97,23 +97,27 @@ def _decode_worker(rank, world, port):
     with torch.cuda.stream(stream):
         tp = DecodeModel.random_init(cfg, seed=7, tp_rank=rank, tp_size=world)
         ref = DecodeModel.random_init(cfg, seed=7, ctx=ops.Context()) if rank == 0 else None
+        # effort 1.0: only the fp32 summation order differs -> tight bar.  effort 0.5: the default engine's reductions have
+        # no fixed order and a row at the cutoff's edge may flip between two runs of the SAME model, so the bar is the
+        # looser one the single-GPU decode tests use for depth
         for use_graph in (False, True):
             tp.set_graphs(use_graph)
-            tp.reset()
-            if rank == 0:
-                ref.reset()
-            for t in (1, 17, 400, 999):
-                tok = torch.tensor([t], dtype=torch.int32, device="cuda")
-                tp.step(tok, 0.5)
-                torch.cuda.synchronize()
-                verdict = [1.0]
+            for effort, bar in ((1.0, 0.99999), (0.5, 0.995)):
+                tp.reset()
                 if rank == 0:
-                    ref.step(tok, 0.5)
+                    ref.reset()
+                for t in (1, 17, 400, 999):
+                    tok = torch.tensor([t], dtype=torch.int32, device="cuda")
+                    tp.step(tok, effort)
                     torch.cuda.synchronize()
-                    a, b = tp.logits().double(), ref.logits().double()
-                    verdict[0] = float((a @ b) / (a.norm() * b.norm()))
-                dist.broadcast_object_list(verdict, src=0)   # every rank fails together: a lone assert strands the peers
-                assert verdict[0] > 0.999, (world, use_graph, t, verdict[0])
+                    verdict = [1.0]
+                    if rank == 0:
+                        ref.step(tok, effort)
+                        torch.cuda.synchronize()
+                        a, b = tp.logits().double(), ref.logits().double()
+                        verdict[0] = float((a @ b) / (a.norm() * b.norm()))
+                    dist.broadcast_object_list(verdict, src=0)   # every rank fails together: a lone assert strands the peers
+                    assert verdict[0] > bar, (world, use_graph, effort, t, verdict[0])
         assert ctx.errorFlag() == 0
     dist.destroy_process_group()
 

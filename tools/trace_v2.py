@@ -1,4 +1,6 @@
-"""Phase timeline of bucket_mul_v2_kernel (EFFORT_TRACE=1): per-CTA globaltimer stamps of one isolated launch."""
+"""Timeline of one isolated launch of the default fused kernel (bucket_mul_v4_kernel).  EFFORT_TRACE=1: per-CTA
+global-timer stamps of the phases + SM-cycle stamps of CTA 0 (prologue steps, every unit of pair 0, when each consumer
+ran dry).  EFFORT_TRACE=2: the cycle stamps only -- the global-timer reads perturb the serial prologue."""
 import argparse, ctypes as C, os, sys
 import numpy as np
 os.environ.setdefault("EFFORT_TRACE", "1")
