@@ -271,7 +271,8 @@ def run_ours(args, rank, local_rank, world):
     stream = torch.cuda.Stream()
     want_quality = rank == 0 and world == 1 and not args.quick and not args.no_quality
     with torch.cuda.stream(stream):
-        cfg = MistralConfig(n_layers=args.layers)
+        # the KV cache must hold every timed position (the C++ loop refuses steps past max_seq, like the reference's maxSeqLen)
+        cfg = MistralConfig(n_layers=args.layers, max_seq=max(2048, args.steps + max(3, args.warmup) + 8))
         if tp:   # one model, column/row sharded over the ranks (same seed everywhere)
             model = DecodeModel.random_init(cfg, seed=1234, tp_rank=rank, tp_size=world)
         else:
